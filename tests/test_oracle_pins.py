@@ -1,0 +1,275 @@
+"""Pins the CPU oracle against every exact-value / known-answer check the reference's own
+test-suite and doctests hold for the dense-grid integration path.
+
+Each test names the reference test it re-expresses (paths relative to /root/reference).
+"""
+import math
+
+import numpy as np
+import pytest
+
+
+def mk(O, f, lc, hc, n, bc=None, dtype=np.float64):
+    fld = O.Field(np.zeros(n, dtype=dtype, order="F"), lc, hc, bc=bc)
+    X = fld.nodes()
+    fld.vals[...] = np.broadcast_to(f(*X), fld.vals.shape).astype(dtype)
+    return fld
+
+
+# ---- src/levelsetops.jl:14-25 and :126-137 (jldoctest scalars) : the only stored numbers ----
+def test_doctest_volume_perimeter_bitexact(O):
+    f = mk(O, lambda x, y: np.sqrt(x * x + y * y) - 0.5, (-1, -1), (1, 1), (200, 200))
+    assert f.volume() == 0.7854362890190668
+    assert f.perimeter() == 3.1426415491430384
+
+
+# ---- test/test-meshes.jl:6-14 ----
+def test_grid_nodes_exact(O):
+    f = mk(O, lambda x, y: x + y, (-1, 0), (1, 3), (100, 50))
+    assert f.getnode((1, 1)) == [-1.0, 0.0]
+    assert f.getnode((100, 50)) == [1.0, 3.0]
+    assert f.meshsize() == [2 / 99, 3 / 49]
+
+
+# ---- test/test-meshfield.jl:44-55 ----
+def test_periodic_getindex_exact(O):
+    rng = np.random.default_rng(0)
+    vals = rng.random((10, 5))
+    mf = O.Field(vals, (0, 0), (1, 1), bc=[O.PERIODIC, O.PERIODIC])
+    assert mf[1, 1] == vals[0, 0]
+    assert mf[1, 0] == vals[0, 3]          # mf[1,0] == vals[1,4] (1-based)
+    assert mf[11, 5] == mf[2, 5]
+    # period is n-1 cells: ghost(1-k) = node(n-k), ghost(n+k) = node(1+k)
+    for k in (1, 2, 3):
+        assert mf[1 - k, 2] == vals[10 - k - 1, 1]
+        assert mf[10 + k, 2] == vals[k, 1]
+
+
+# ---- test/test-meshfield.jl:57-98 ----
+def test_extrapolation_getindex(O):
+    a, b, n = -0.3, 1.7, 10
+    h = (b - a) / (n - 1)
+    for P in range(0, 6):
+        for k in range(0, P + 1):
+            f = mk(O, lambda x: x ** k, (a,), (b,), (n,), bc=[O.EXTRAP(P)])
+            for j in range(1, P + 2):
+                assert f[1 - j] == pytest.approx((a - j * h) ** k, abs=1e-10)
+                assert f[n + j] == pytest.approx((b + j * h) ** k, abs=1e-10)
+    a1, a2, b1, b2, n1, n2 = -0.3, 0.5, 1.7, 2.1, 8, 6
+    h1, h2 = (b1 - a1) / (n1 - 1), (b2 - a2) / (n2 - 1)
+    for P in (1, 2, 3):
+        for j in range(P + 1):
+            for k in range(P + 1):
+                g = lambda x, y: x ** j * y ** k
+                f = mk(O, g, (a1, a2), (b1, b2), (n1, n2), bc=[O.EXTRAP(P), O.EXTRAP(P)])
+                y3 = f.getnode((1, 3))[1]
+                assert f[0, 3] == pytest.approx(g(a1 - h1, y3), abs=1e-10)
+                assert f[n1 + 1, 3] == pytest.approx(g(b1 + h1, y3), abs=1e-10)
+                assert f[0, 0] == pytest.approx(g(a1 - h1, a2 - h2), abs=1e-10)
+                assert f[n1 + 1, n2 + 1] == pytest.approx(g(b1 + h1, b2 + h2), abs=1e-10)
+
+
+def test_extrapolation_weight_table():
+    """SURVEY.md §8a table for w_j(k,P) (boundaryconditions.jl:90-97) via ghost reads of unit vectors."""
+    import oracle as O
+    table = {(0, 1): [1], (1, 1): [2, -1], (1, 2): [3, -2], (1, 3): [4, -3],
+             (2, 1): [3, -3, 1], (2, 2): [6, -8, 3], (2, 3): [10, -15, 6],
+             (3, 1): [4, -6, 4, -1], (3, 2): [10, -20, 15, -4], (3, 3): [20, -45, 36, -10]}
+    n = 8
+    for (P, k), w in table.items():
+        for j, wj in enumerate(w):
+            e = np.zeros(n); e[j] = 1.0
+            assert O.Field(e, (0,), (1,), bc=[O.EXTRAP(P)])[1 - k] == pytest.approx(wj, abs=1e-12)
+            e = np.zeros(n); e[n - 1 - j] = 1.0
+            assert O.Field(e, (0,), (1,), bc=[O.EXTRAP(P)])[n + k] == pytest.approx(wj, abs=1e-12)
+
+
+# ---- test/test-meshfield.jl:100-125 ----
+def test_symmetry_getindex(O):
+    f = mk(O, lambda x: x, (0.0,), (4.0,), (5,), bc=[O.SYMMETRY])
+    fn = mk(O, lambda x: x, (0.0,), (4.0,), (5,), bc=[O.NEUMANN])
+    assert f[0] == 1.0 and f[-1] == 2.0 and f[6] == 3.0 and f[7] == 2.0
+    assert fn[0] == 0.0 and f[0] != fn[0]
+    g = mk(O, lambda x: x * x, (0.0,), (4.0,), (5,), bc=[O.SYMMETRY])
+    assert g[0] == pytest.approx(1.0) and g[-1] == pytest.approx(4.0)
+    f2 = mk(O, lambda x, y: x + 10 * y, (0.0, 0.0), (4.0, 4.0), (5, 5), bc=[O.SYMMETRY, O.SYMMETRY])
+    assert f2[0, 0] == f2[2, 2]
+
+
+# ---- test/test-boundaryconditions.jl ----
+def test_normalize_bc(O):
+    P, N, E2 = O.PERIODIC, O.NEUMANN, O.EXTRAP(2)
+    assert O._norm_bc(P, 2) == [(P, P), (P, P)]
+    assert O._norm_bc([P, N], 2) == [(P, P), (N, N)]
+    r = O._norm_bc([P, (E2, N)], 2)
+    assert r[0] == (P, P) and r[1] == (E2, N)
+    with pytest.raises(ValueError):
+        O._norm_bc([(P, E2), (E2, N)], 2)
+
+
+# ---- test/test-derivatives.jl:15-42 ----
+def test_derivative_stencils(O):
+    f = mk(O, lambda x, y: x ** 3 + x * y ** 2, (-2.0, -2.0), (2.0, 2.0), (400, 200))
+    h = f.meshsize()
+    I = (9, 7)
+    x, y = f.getnode(I)
+    exact = (3 * x * x + y * y, 2 * x * y)
+    for dim in (1, 2):
+        hd = h[dim - 1]
+        assert abs(f.deriv("D+", I, dim) - exact[dim - 1]) < 10 * hd
+        assert abs(f.deriv("D-", I, dim) - exact[dim - 1]) < 10 * hd
+        assert abs(f.deriv("D0", I, dim) - exact[dim - 1]) < 5 * hd ** 2
+        assert abs(f.deriv("weno5-", I, dim) - exact[dim - 1]) < 5 * hd ** 2
+        assert abs(f.deriv("weno5+", I, dim) - exact[dim - 1]) < 5 * hd ** 2
+    diag = (6 * x, 2 * x)
+    for dim in (1, 2):
+        hd = h[dim - 1]
+        assert abs(f.deriv("D2_0", I, dim) - diag[dim - 1]) < 5 * hd
+        assert abs(f.deriv("D2++", I, dim) - diag[dim - 1]) < 10 * hd
+        assert abs(f.deriv("D2--", I, dim) - diag[dim - 1]) < 10 * hd
+    for d1, d2 in ((1, 2), (2, 1)):
+        assert abs(f.deriv("D2", I, d1, d2) - 2 * y) < 5 * h[0] * h[1]
+
+
+def test_weno5_known_answers(O):
+    L = O.lib()
+    # linear data: every candidate equals the common slope; smooth weights are the ideal ones
+    assert L.orc_weno5(2.0, 2.0, 2.0, 2.0, 2.0) == pytest.approx(2.0, rel=1e-15)
+    # flat data must give finite (zero) result thanks to the 1e-99 floor (test-levelsetterms.jl:53-77)
+    assert L.orc_weno5(0.0, 0.0, 0.0, 0.0, 0.0) == 0.0
+    # linear-in-i data v_i = i: all three third-order candidates equal 3.5, so any convex combination is 3.5
+    assert L.orc_weno5(1.0, 2.0, 3.0, 4.0, 5.0) == pytest.approx(3.5, rel=1e-15)
+    # a shock on the right: weight collapses onto the left candidate d1 = 1/3 v1 - 7/6 v2 + 11/6 v3
+    v = (1.0, 1.0, 1.0, 1.0, 1000.0)
+    assert L.orc_weno5(*v) == pytest.approx(1.0, rel=1e-6)
+    # minmod limiter (levelsetterms.jl:184-187)
+    assert L.orc_limiter(1.0, 2.0) == 1.0 and L.orc_limiter(-3.0, -2.0) == -2.0
+    assert L.orc_limiter(1.0, -2.0) == 0.0 and L.orc_limiter(0.0, 5.0) == 0.0
+
+
+# ---- test/test-levelsetterms.jl:7-31 ----
+def test_cfl_closed_forms(O):
+    f = mk(O, lambda x: x, (-1.0,), (1.0,), (100,))
+    dx = f.meshsize(1)
+    assert O.compute_cfl(f, [O.advection((2.0,))]) == pytest.approx(dx / 2.0, rel=1e-15)
+    assert O.compute_cfl(f, [O.normal_motion(3.0)]) == pytest.approx(dx / 3.0, rel=1e-15)
+    g = mk(O, lambda x, y: np.sqrt(x * x + y * y) - 0.5, (-1.0, -1.0), (1.0, 1.0), (50, 50))
+    dxm = min(g.meshsize())
+    assert O.compute_cfl(g, [O.curvature(0.5)]) == pytest.approx(dxm ** 2 / (2 * 0.5), rel=1e-15)
+    # min over terms; stored velocity field; NaN / zero velocity semantics
+    u = np.zeros((2, 50, 50), order="F"); u[0] = 1.0; u[1] = -3.0
+    hx, hy = g.meshsize()
+    assert O.compute_cfl(g, [O.advection(u), O.curvature(1e-9)]) == 1 / (1.0 / hx + 3.0 / hy)
+    assert O.compute_cfl(g, [O.advection(np.zeros_like(u))]) == math.inf
+    u[0, 3, 4] = np.nan
+    with pytest.raises(O.CFLError):
+        O.compute_cfl(g, [O.advection(u)])
+    u[0, 3, 4] = np.inf
+    with pytest.raises(O.CFLError):
+        O.compute_cfl(g, [O.advection(u)])
+
+
+# ---- test/test-levelsetterms.jl:33-51 ----
+def test_eikonal_1d_reinit(O):
+    f = mk(O, lambda x: 2 * (x - 0.3), (-1.0,), (1.0,), (101,), bc=[O.EXTRAP(1)])
+    s0 = O.eikonal_s0(f)
+    O.integrate(f, O.RK2, [O.eikonal(s0)], 2.0)
+    x = f.nodes()[0]
+    err = np.where(np.abs(f.vals) > 0.5, 0.0, np.abs(f.vals - (x - 0.3))).max()
+    assert err < 0.05
+
+
+# ---- test/test-levelsetterms.jl:53-77 ----
+def test_nan_robustness(O):
+    f = mk(O, lambda x, y: np.sqrt(x * x + y * y) - 0.7, (-2.0, -2.0), (2.0, 2.0), (31, 31), bc=O.NEUMANN)
+    O.integrate(f, O.RK2, [O.curvature(-0.1)], 0.1)
+    assert not np.isnan(f.vals).any()
+    g = mk(O, lambda x: 0.0 * x, (-1.0,), (1.0,), (31,), bc=O.NEUMANN)
+    O.integrate(g, O.RK2, [O.eikonal()], 0.1)
+    assert not np.isnan(g.vals).any()
+    # flat field under WENO5 advection stays finite too (epsilon floor)
+    hflat = mk(O, lambda x: 0.0 * x + 1.0, (-1.0,), (1.0,), (31,), bc=O.PERIODIC)
+    O.integrate(hflat, O.RK3, [O.advection((1.0,))], 0.1)
+    assert np.all(hflat.vals == 1.0)
+
+
+# ---- test/test-timestepping.jl:8-46 ----
+def _adv_err_1d(O, integ, N, u=1.0, tf=0.5, cfl=0.5, scheme=None):
+    f = mk(O, lambda x: np.sin(np.pi * x), (-1.0,), (1.0,), (N,), bc=O.PERIODIC)
+    sch = O.WENO5 if scheme is None else scheme
+    O.integrate(f, integ, [O.advection((u,), scheme=sch)], tf, cfl=cfl)
+    x = f.nodes()[0]
+    return np.abs(f.vals - np.sin(np.pi * (x - u * tf))).max()
+
+
+def test_timestepping_accuracy(O):
+    assert _adv_err_1d(O, O.FE, 200) < 0.05
+    assert _adv_err_1d(O, O.RK2, 200) < 1.0e-3
+    assert _adv_err_1d(O, O.RK3, 200) < 1.0e-5
+
+
+def test_timestepping_orders(O):
+    Ns = [50, 100, 200, 400]
+    for integ, p in ((O.FE, 1), (O.RK2, 2), (O.RK3, 3)):
+        e = [_adv_err_1d(O, integ, N) for N in Ns]
+        for i in range(len(Ns) - 1):
+            assert math.log(e[i] / e[i + 1]) / math.log(Ns[i + 1] / Ns[i]) >= p - 0.5
+
+
+# ---- test/test-levelsetequation.jl:26-65 ----
+def test_weno5_and_upwind_spatial_order(O):
+    Ns = [20, 40, 80]
+    e = [_adv_err_1d(O, O.RK3, N, cfl=1e-2) for N in Ns]
+    assert all(math.log(e[i] / e[i + 1]) / math.log(2) >= 4.5 for i in range(2))
+    Ns = [50, 100, 200]
+    e = [_adv_err_1d(O, O.RK3, N, cfl=1e-2, scheme=O.UPWIND) for N in Ns]
+    assert all(math.log(e[i] / e[i + 1]) / math.log(2) >= 0.8 for i in range(2))
+
+
+# ---- test/test-levelsetequation.jl:67-119 ----
+def test_normal_motion_and_curvature_order(O):
+    def run(N, term, exact):
+        f = mk(O, lambda x, y: np.sqrt(x * x + y * y) - r0, (-2.0, -2.0), (2.0, 2.0), (N, N), bc=O.EXTRAP(2))
+        O.integrate(f, O.RK3, [term], 0.2)
+        x, y = f.nodes()
+        r = np.sqrt(x * x + y * y)
+        return np.where((r >= 0.5) & (r <= 1.5), np.abs(f.vals - exact(r)), 0.0).max()
+
+    r0, v, tf = 0.5, 0.5, 0.2
+    e = [run(N, O.normal_motion(v), lambda r: r - r0 - v * tf) for N in (30, 60, 120)]
+    assert all(math.log(e[i] / e[i + 1]) / math.log(2) >= 1.5 for i in range(2))
+    r0, b = 0.7, -0.1
+    e = [run(N, O.curvature(b), lambda r: np.sqrt(r * r - 2 * b * tf) - r0) for N in (30, 60, 120)]
+    assert all(math.log(e[i] / e[i + 1]) / math.log(2) >= 1.5 for i in range(2))
+
+
+# ---- src/levelsetequation.jl:194-203 / timestepping.jl:101-122 : loop semantics ----
+def test_integrate_loop_semantics(O):
+    f = mk(O, lambda x: np.sin(np.pi * x), (-1.0,), (1.0,), (101,), bc=O.PERIODIC)
+    h = f.meshsize(1)
+    t, steps = O.integrate(f, O.RK3, [O.advection((1.0,))], 0.5)
+    assert t == 0.5 and steps == math.ceil(0.5 / (0.5 * h) - 1e-9)
+    with pytest.raises(ValueError):
+        O.integrate(f, O.RK3, [O.advection((1.0,))], -1.0)
+    # tf == t0 : zero steps, state untouched
+    before = f.vals.copy()
+    t, steps = O.integrate(f, O.RK3, [O.advection((1.0,))], 0.5, t0=0.5)
+    assert steps == 0 and np.array_equal(before, f.vals)
+    # dt_max caps the step
+    t, steps = O.integrate(f, O.FE, [O.advection((1.0,))], 0.01, dt_max=0.001)
+    assert steps in (10, 11)
+
+
+def test_stage_api_equals_advance(O):
+    """orc_stage x nstages == orc_advance, for all three integrators, two terms."""
+    rng = np.random.default_rng(1)
+    for integ in (O.FE, O.RK2, O.RK3):
+        f = mk(O, lambda x, y: np.sqrt(x * x + y * y) - 0.5, (-1, -1), (1, 1), (24, 20), bc=O.NEUMANN)
+        g = O.Field(f.vals.copy(order="F"), (-1, -1), (1, 1), bc=O.NEUMANN)
+        u = np.asfortranarray(rng.standard_normal((2, 24, 20)))
+        terms = [O.advection(u), O.curvature(-0.01)]
+        O.advance(f, integ, terms, 0.0, 1e-3)
+        b1, b2 = g.vals.copy(order="F"), g.vals.copy(order="F")
+        for s in range(1, O.nstages(integ) + 1):
+            O.stage(g, integ, s, b1, b2, terms, 0.0, 1e-3)
+        assert np.array_equal(f.vals, g.vals)
