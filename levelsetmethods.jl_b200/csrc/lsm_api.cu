@@ -1,0 +1,883 @@
+// lsm_api.cu — implementation of the C ABI declared in include/lsm_b200.h.
+//
+// Host-side runtime of the engine: contexts (one process == one GPU == one rank), device
+// fields with ghost planes for slab decomposition, NCCL halo exchange overlapped with interior
+// compute, the CFL cache, and the step loop of _integrate! (timestepping.jl:101-122).
+// No CPU fallback exists: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lsm_b200.h"
+#include "lsm_dev.cuh"
+#include "lsm_kernels.h"
+#include "nccl_dyn.h"
+
+using namespace lsm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int32_t fail(int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) \
+    return fail(e_ == cudaErrorMemoryAllocation ? LSM_ERR_OOM : LSM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define NC(expr) do { ncclResult_t r_ = (expr); if (r_ != ncclSuccess) \
+    return fail(LSM_ERR_NCCL, "%s failed: %s (%s:%d)", #expr, nccl().GetErrorString ? nccl().GetErrorString(r_) : "?", __FILE__, __LINE__); } while (0)
+#define TRY(expr) do { int32_t rc_ = (expr); if (rc_ != LSM_OK) return rc_; } while (0)
+
+constexpr int HALO = 3;    // ghost planes per side of the decomposed axis (WENO5 reach)
+
+inline double jl_min(double a, double b) {
+    return (std::isnan(a) || std::isnan(b)) ? std::numeric_limits<double>::quiet_NaN() : (b < a ? b : a);
+}
+inline double jl_eps(double x) {    // Base.eps(::Float64)
+    x = std::fabs(x);
+    return std::nextafter(x, std::numeric_limits<double>::infinity()) - x;
+}
+
+struct CflCacheEntry { int kind; const void* field; uint64_t version; double g; int scaled; unsigned long long bits; };
+
+}  // namespace
+
+struct lsm_ctx {
+    int device = 0, rank = 0, nranks = 1, sm_count = 148;
+    cudaStream_t stream = nullptr, comm = nullptr;
+    cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
+    ncclComm_t nccl_comm = nullptr;
+    unsigned long long* d_scalar = nullptr;     // device scalar for reductions
+    unsigned long long* h_scalar = nullptr;     // pinned
+    lsm_counters cnt{};
+    int opt_kernel = 0, opt_time = 0, opt_cfl_cache = 1, opt_overlap = 1;
+    std::vector<CflCacheEntry> cfl_cache;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;     // pending stage timings
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+struct lsm_field {
+    lsm_ctx* ctx = nullptr;
+    int ndim = 0, dtype = LSM_F64, ncomp = 1;
+    int nglob[3] = {1, 1, 1}, n[3] = {1, 1, 1};
+    int first_last = 0;          // global 0-based index of the first owned plane of the last dim
+    int halo = 0;                // stored ghost planes per side (last dim)
+    double lc[3] = {0, 0, 0}, hc[3] = {1, 1, 1}, h[3] = {1, 1, 1};
+    lsm_bc bc[3][2];
+    bool has_bc = false;
+    void* base = nullptr;        // allocation start
+    void* p = nullptr;           // first owned node
+    long plane = 1;              // elements per plane of the last dim
+    long owned = 1;              // owned elements per component
+    long cstride = 0;            // component stride (SoA)
+    uint64_t version = 1;
+    bool halo_valid = false;
+    lsm_field* buf1 = nullptr;   // RK stage buffers (timestepping.jl:126,141,168)
+    lsm_field* buf2 = nullptr;
+    // separable coefficient
+    bool separable = false;
+    double scale[3] = {1, 1, 1};
+    double* d_tabs = nullptr;
+    const double* tab[3][3] = {};
+};
+
+namespace {
+
+size_t esize(int dtype) { return dtype == LSM_F32 ? 4 : 8; }
+
+int32_t ctx_common_init(lsm_ctx* c) {
+    CU(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major < 10) return fail(LSM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", c->device, prop.major, prop.minor);
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->comm, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_boundary, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+    CU(cudaMalloc(&c->d_scalar, 64));
+    CU(cudaMallocHost(&c->h_scalar, 64));
+    return LSM_OK;
+}
+
+void slab_plan(int n_last, int nranks, int rank, int* first, int* count) {
+    const int base = n_last / nranks, rem = n_last % nranks;
+    *count = base + (rank < rem ? 1 : 0);
+    *first = rank * base + (rank < rem ? rank : rem);
+}
+
+int32_t field_alloc(lsm_ctx* ctx, int ndim, const int32_t* n, int dtype, int ncomp, const double* lc, const double* hc,
+                    bool with_halo, lsm_field** out) {
+    if (!ctx || !n || !out) return fail(LSM_ERR_ARG, "null argument");
+    if (ndim < 1 || ndim > 3) return fail(LSM_ERR_ARG, "ndim must be 1, 2 or 3 (got %d)", ndim);
+    if (dtype != LSM_F32 && dtype != LSM_F64) return fail(LSM_ERR_ARG, "bad dtype %d", dtype);
+    if (ncomp != 1 && ncomp != ndim) return fail(LSM_ERR_ARG, "ncomp must be 1 or ndim");
+    lsm_field* f = new (std::nothrow) lsm_field();
+    if (!f) return fail(LSM_ERR_OOM, "host allocation failed");
+    f->ctx = ctx; f->ndim = ndim; f->dtype = dtype; f->ncomp = ncomp;
+    for (int d = 0; d < 3; ++d) {
+        f->nglob[d] = d < ndim ? n[d] : 1;
+        f->n[d] = f->nglob[d];
+        f->lc[d] = (d < ndim && lc) ? lc[d] : 0.0;
+        f->hc[d] = (d < ndim && hc) ? hc[d] : 1.0;
+        if (d < ndim && n[d] < 1) { delete f; return fail(LSM_ERR_ARG, "n[%d] = %d", d, n[d]); }
+        f->h[d] = d < ndim ? (f->hc[d] - f->lc[d]) / double(f->nglob[d] - 1) : 1.0;    // meshes.jl:109-110
+        f->bc[d][0] = {LSM_BC_NONE, 0}; f->bc[d][1] = {LSM_BC_NONE, 0};
+    }
+    const int last = ndim - 1;
+    int first = 0, count = f->nglob[last];
+    if (ctx->nranks > 1) {
+        slab_plan(f->nglob[last], ctx->nranks, ctx->rank, &first, &count);
+        if (count < HALO + 1) { delete f; return fail(LSM_ERR_ARG, "slab of %d planes is thinner than %d; use fewer ranks", count, HALO + 1); }
+    }
+    f->first_last = first; f->n[last] = count;
+    f->plane = 1; for (int d = 0; d < last; ++d) f->plane *= f->n[d];
+    f->owned = f->plane * f->n[last];
+    f->halo = (with_halo && ctx->nranks > 1 && ncomp == 1) ? HALO : 0;
+    const long per_comp = f->owned + 2L * f->halo * f->plane;
+    f->cstride = per_comp;
+    cudaError_t e = cudaMalloc(&f->base, (size_t)per_comp * ncomp * esize(dtype));
+    if (e != cudaSuccess) { delete f; return fail(e == cudaErrorMemoryAllocation ? LSM_ERR_OOM : LSM_ERR_CUDA, "cudaMalloc of %.1f MB failed: %s", per_comp * ncomp * esize(dtype) / 1e6, cudaGetErrorString(e)); }
+    f->p = static_cast<char*>(f->base) + (size_t)f->halo * f->plane * esize(dtype);
+    if (f->halo) cudaMemsetAsync(f->base, 0, (size_t)per_comp * esize(dtype), ctx->stream);
+    *out = f;
+    return LSM_OK;
+}
+
+void field_free(lsm_field* f) {
+    if (!f) return;
+    if (f->buf1) field_free(f->buf1);
+    if (f->buf2) field_free(f->buf2);
+    if (f->base) cudaFree(f->base);
+    if (f->d_tabs) cudaFree(f->d_tabs);
+    delete f;
+}
+
+int32_t ensure_buffers(lsm_field* phi, int nbuf) {
+    lsm_field** slots[2] = {&phi->buf1, &phi->buf2};
+    for (int b = 0; b < nbuf; ++b) {
+        if (*slots[b]) continue;
+        lsm_field* nb = nullptr;
+        TRY(field_alloc(phi->ctx, phi->ndim, phi->nglob, phi->dtype, 1, phi->lc, phi->hc, true, &nb));
+        std::memcpy(nb->bc, phi->bc, sizeof phi->bc);
+        nb->has_bc = phi->has_bc;
+        *slots[b] = nb;
+    }
+    return LSM_OK;
+}
+
+template <class T>
+View<T> make_view(const lsm_field* f) {
+    View<T> v;
+    v.p = static_cast<const T*>(f->p);
+    for (int d = 0; d < 3; ++d) v.n[d] = f->n[d];
+    v.s1 = f->ndim > 1 ? (long)f->n[0] : 0;
+    v.s2 = f->ndim > 2 ? (long)f->n[0] * f->n[1] : 0;
+    const lsm_ctx* c = f->ctx;
+    const int last = f->ndim - 1;
+    for (int d = 0; d < 3; ++d)
+        for (int s = 0; s < 2; ++s) { v.bc[d][s].kind = f->bc[d][s].kind; v.bc[d][s].P = f->bc[d][s].P; }
+    if (c->nranks > 1 && f->halo) {
+        const bool periodic = f->bc[last][0].kind == LSM_BC_PERIODIC;
+        if (c->rank > 0 || periodic) v.bc[last][0].kind = BC_HALO;
+        if (c->rank < c->nranks - 1 || periodic) v.bc[last][1].kind = BC_HALO;
+    }
+    return v;
+}
+
+double term_scale(const lsm_term& t, double time, const double* gscale, int k) {
+    switch (t.tscale_kind) {
+        case LSM_TS_COS:  return std::cos(M_PI * time / t.tparam);
+        case LSM_TS_HOST: return gscale ? gscale[k] : 1.0;
+        default:          return 1.0;
+    }
+}
+
+int32_t make_term_dev(const lsm_field* phi, const lsm_term& t, double g, TermDev* out) {
+    TermDev d{};
+    if (t.kind < LSM_TERM_ADVECTION || t.kind > LSM_TERM_EIKONAL) return fail(LSM_ERR_ARG, "bad term kind %d", t.kind);
+    d.kind = t.kind; d.scheme = t.scheme; d.coef_kind = t.coef_kind;
+    d.scaled = t.tscale_kind != LSM_TS_NONE; d.g = g;
+    for (int i = 0; i < 3; ++i) d.cval[i] = t.cval[i];
+    if (t.kind == LSM_TERM_ADVECTION && t.scheme != LSM_UPWIND && t.scheme != LSM_WENO5) return fail(LSM_ERR_ARG, "bad scheme %d", t.scheme);
+    if (t.kind == LSM_TERM_EIKONAL && t.coef_kind != LSM_COEF_NONE && t.coef_kind != LSM_COEF_FIELD)
+        return fail(LSM_ERR_ARG, "eikonal term takes a frozen S0 field or no coefficient");
+    if (t.kind != LSM_TERM_EIKONAL && t.coef_kind == LSM_COEF_NONE) return fail(LSM_ERR_ARG, "term %d needs a coefficient", t.kind);
+    if (t.coef_kind == LSM_COEF_FIELD || t.coef_kind == LSM_COEF_SEPARABLE) {
+        const lsm_field* cf = t.field;
+        if (!cf) return fail(LSM_ERR_ARG, "coefficient field is NULL");
+        if (cf->ctx != phi->ctx) return fail(LSM_ERR_ARG, "coefficient field belongs to another context");
+        const int want = t.kind == LSM_TERM_ADVECTION ? phi->ndim : 1;
+        if (cf->ndim != phi->ndim || cf->ncomp != want) return fail(LSM_ERR_ARG, "coefficient field has ndim=%d ncomp=%d, expected %d/%d", cf->ndim, cf->ncomp, phi->ndim, want);
+        for (int a = 0; a < phi->ndim; ++a)
+            if (cf->nglob[a] != phi->nglob[a]) return fail(LSM_ERR_ARG, "coefficient field shape mismatch along dim %d", a + 1);
+        if (t.coef_kind == LSM_COEF_SEPARABLE) {
+            if (!cf->separable) return fail(LSM_ERR_ARG, "LSM_COEF_SEPARABLE needs a field from lsm_field_create_separable");
+            for (int c = 0; c < 3; ++c) { d.cval[c] = cf->scale[c]; for (int a = 0; a < 3; ++a) d.tab[c][a] = cf->tab[c][a]; }
+        } else {
+            if (cf->separable) return fail(LSM_ERR_ARG, "separable field passed as LSM_COEF_FIELD");
+            if (cf->dtype != phi->dtype) {
+                if (cf->dtype == LSM_F64 && phi->dtype == LSM_F32) d.coef_f64 = 1;
+                else return fail(LSM_ERR_UNSUPPORTED, "Float32 coefficient with a Float64 state is not supported");
+            }
+            d.coef = cf->p; d.cstride = cf->cstride;
+        }
+    }
+    *out = d;
+    return LSM_OK;
+}
+
+// ---- halo exchange: whole contiguous planes of the decomposed (last) axis -------
+int32_t exchange_halo(lsm_field* f, cudaStream_t s) {
+    lsm_ctx* c = f->ctx;
+    if (c->nranks == 1 || !f->halo) { f->halo_valid = true; return LSM_OK; }
+    const int last = f->ndim - 1;
+    const bool periodic = f->bc[last][0].kind == LSM_BC_PERIODIC;
+    const size_t es = esize(f->dtype);
+    const size_t bytes = (size_t)HALO * f->plane * es;
+    char* p = static_cast<char*>(f->p);
+    const int nl = f->n[last], R = c->rank, G = c->nranks;
+    auto plane_ptr = [&](int k) { return p + (ptrdiff_t)k * (ptrdiff_t)f->plane * (ptrdiff_t)es; };
+    NC(nccl().GroupStart());
+    // to the upper neighbour: my top planes -> its low ghosts; from it: its bottom planes -> my high ghosts
+    if (R + 1 < G) {
+        NC(nccl().Send(plane_ptr(nl - HALO), bytes, ncclInt8, R + 1, c->nccl_comm, s));
+        NC(nccl().Recv(plane_ptr(nl), bytes, ncclInt8, R + 1, c->nccl_comm, s));
+        c->cnt.halo_bytes_sent += (int64_t)bytes;
+    } else if (periodic) {
+        // wrap honouring the reference's periodic rule (boundaryconditions.jl:107-119): node n duplicates
+        // node 1, so ghost(n+k) = node(1+k): rank 0's planes 1..3; and my planes nl-4..nl-2 are rank 0's low ghosts
+        NC(nccl().Send(plane_ptr(nl - 1 - HALO), bytes, ncclInt8, 0, c->nccl_comm, s));
+        NC(nccl().Recv(plane_ptr(nl), bytes, ncclInt8, 0, c->nccl_comm, s));
+        c->cnt.halo_bytes_sent += (int64_t)bytes;
+    }
+    if (R > 0) {
+        NC(nccl().Send(plane_ptr(0), bytes, ncclInt8, R - 1, c->nccl_comm, s));
+        NC(nccl().Recv(plane_ptr(-HALO), bytes, ncclInt8, R - 1, c->nccl_comm, s));
+        c->cnt.halo_bytes_sent += (int64_t)bytes;
+    } else if (periodic) {
+        NC(nccl().Send(plane_ptr(1), bytes, ncclInt8, G - 1, c->nccl_comm, s));
+        NC(nccl().Recv(plane_ptr(-HALO), bytes, ncclInt8, G - 1, c->nccl_comm, s));
+        c->cnt.halo_bytes_sent += (int64_t)bytes;
+    }
+    NC(nccl().GroupEnd());
+    f->halo_valid = true;
+    return LSM_OK;
+}
+
+cudaEvent_t pool_event(lsm_ctx* c) {
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr; cudaEventCreate(&e); return e;
+}
+
+void resolve_timings(lsm_ctx* c) {
+    if (c->timed.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& pr : c->timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+            c->cnt.last_stage_ms = ms; c->cnt.sum_stage_ms += ms; c->cnt.timed_stages += 1;
+        }
+        c->ev_pool.push_back(pr.first); c->ev_pool.push_back(pr.second);
+    }
+    c->timed.clear();
+}
+
+template <class T>
+int32_t launch_stage_range(lsm_ctx* c, int ndim, StageParams<T>& P, int r0, int r1) {
+    if (r1 <= r0) return LSM_OK;
+    P.r0 = r0; P.r1 = r1;
+    cudaError_t e = cudaErrorNotSupported;
+    if (c->opt_kernel != 1 && stage_tiled_supported<T>(ndim, P)) e = launch_stage_tiled<T>(ndim, P, c->sm_count, c->stream);
+    else if (c->opt_kernel == 2) return fail(LSM_ERR_UNSUPPORTED, "tiled kernel forced but this configuration is not covered");
+    if (e == cudaErrorNotSupported) e = launch_stage_generic<T>(ndim, P, c->stream);
+    if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "stage kernel launch failed: %s", cudaGetErrorString(e));
+    c->cnt.kernel_launches += 1; c->cnt.stage_launches += 1;
+    return LSM_OK;
+}
+
+// One fused RK stage: out = base(in, p0) - c * sum_k H_k(in), written in the reference's rounding
+// order, with the output's halo exchange overlapped with the interior update.
+template <class T>
+int32_t run_stage_t(lsm_ctx* c, lsm_field* in, lsm_field* p0, lsm_field* out, lsm_field* out2, int base, double cc, double c2,
+                    const lsm_term* terms, int nterms, double tstage, const double* gscale, bool out_needs_halo) {
+    StageParams<T> P{};
+    P.in = make_view<T>(in);
+    P.p0 = p0 ? static_cast<const T*>(p0->p) : nullptr;
+    P.out = static_cast<T*>(out->p);
+    P.out2 = out2 ? static_cast<T*>(out2->p) : nullptr;
+    P.base = base; P.nterms = nterms; P.c = cc; P.c2 = c2;
+    double dxmin = in->h[0];
+    for (int d = 0; d < 3; ++d) { P.h[d] = in->h[d]; if (d < in->ndim) dxmin = std::min(dxmin, in->h[d]); }
+    P.dxmin = dxmin;
+    for (int k = 0; k < nterms; ++k) TRY(make_term_dev(in, terms[k], term_scale(terms[k], tstage, gscale, k), &P.terms[k]));
+
+    const int last = in->ndim - 1, nl = in->n[last];
+    if (c->nranks > 1 && !in->halo_valid) {        // e.g. right after an upload
+        TRY(exchange_halo(in, c->stream));
+    }
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (c->opt_time) { t0 = pool_event(c); t1 = pool_event(c); cudaEventRecord(t0, c->stream); }
+    if (c->nranks > 1 && out_needs_halo && c->opt_overlap && nl >= 4 * HALO) {
+        // boundary slabs first, then ship them while the interior is computed
+        TRY(launch_stage_range<T>(c, in->ndim, P, 0, HALO + 1));
+        TRY(launch_stage_range<T>(c, in->ndim, P, nl - HALO - 1, nl));
+        CU(cudaEventRecord(c->ev_boundary, c->stream));
+        CU(cudaStreamWaitEvent(c->comm, c->ev_boundary, 0));
+        TRY(exchange_halo(out, c->comm));
+        CU(cudaEventRecord(c->ev_halo, c->comm));
+        TRY(launch_stage_range<T>(c, in->ndim, P, HALO + 1, nl - HALO - 1));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+    } else {
+        TRY(launch_stage_range<T>(c, in->ndim, P, 0, nl));
+        if (c->nranks > 1 && out_needs_halo) TRY(exchange_halo(out, c->stream));
+    }
+    if (c->opt_time) { cudaEventRecord(t1, c->stream); c->timed.emplace_back(t0, t1); }
+    out->version++; out->halo_valid = (c->nranks == 1) || out_needs_halo;
+    if (out2) { out2->version++; out2->halo_valid = (c->nranks == 1); }
+    return LSM_OK;
+}
+
+int32_t run_stage(lsm_ctx* c, lsm_field* in, lsm_field* p0, lsm_field* out, lsm_field* out2, int base, double cc, double c2,
+                  const lsm_term* terms, int nterms, double tstage, const double* gscale, bool out_needs_halo) {
+    if (in->dtype == LSM_F64) return run_stage_t<double>(c, in, p0, out, out2, base, cc, c2, terms, nterms, tstage, gscale, out_needs_halo);
+    return run_stage_t<float>(c, in, p0, out, out2, base, cc, c2, terms, nterms, tstage, gscale, out_needs_halo);
+}
+
+void swap_storage(lsm_field* a, lsm_field* b) {
+    std::swap(a->base, b->base); std::swap(a->p, b->p);
+    std::swap(a->halo_valid, b->halo_valid);
+    a->version++; b->version++;
+}
+
+int32_t check_state(lsm_ctx* ctx, lsm_field* phi, const lsm_term* terms, int nterms) {
+    if (!ctx || !phi || !terms) return fail(LSM_ERR_ARG, "null argument");
+    if (phi->ctx != ctx) return fail(LSM_ERR_ARG, "field belongs to another context");
+    if (nterms < 1 || nterms > LSM_MAX_TERMS) return fail(LSM_ERR_ARG, "nterms must be in 1..%d", LSM_MAX_TERMS);
+    if (phi->ncomp != 1 || phi->separable) return fail(LSM_ERR_ARG, "the state must be a scalar field");
+    if (!phi->has_bc) return fail(LSM_ERR_BC, "no boundary conditions: call lsm_field_set_bc on the state");   // levelsetequation.jl:69-70
+    CU(cudaSetDevice(ctx->device));
+    return LSM_OK;
+}
+
+int32_t stage_impl(lsm_ctx* ctx, int integ, int stage, lsm_field* phi, const lsm_term* terms, int nterms, double tc, double dt, const double* gs) {
+    switch (integ) {
+        case LSM_FORWARD_EULER:      // timestepping.jl:128-137
+            if (stage != 1) return fail(LSM_ERR_ARG, "ForwardEuler has 1 stage");
+            TRY(ensure_buffers(phi, 1));
+            TRY(run_stage(ctx, phi, nullptr, phi->buf1, nullptr, BASE_IN, dt, 0, terms, nterms, tc, gs, true));
+            swap_storage(phi, phi->buf1);          // copy!(phi, dst) without the copy
+            return LSM_OK;
+        case LSM_RK2:                // timestepping.jl:143-164
+            TRY(ensure_buffers(phi, 2));
+            if (stage == 1) return run_stage(ctx, phi, nullptr, phi->buf1, phi->buf2, BASE_IN, dt, 0.5 * dt, terms, nterms, tc, gs, true);
+            if (stage == 2) return run_stage(ctx, phi->buf1, phi->buf2, phi, nullptr, BASE_P0, 0.5 * dt, 0, terms, nterms, tc + dt, gs, true);
+            return fail(LSM_ERR_ARG, "RK2 has 2 stages");
+        case LSM_RK3:                // timestepping.jl:170-202
+            TRY(ensure_buffers(phi, 2));
+            if (stage == 1) return run_stage(ctx, phi, nullptr, phi->buf1, nullptr, BASE_IN, dt, 0, terms, nterms, tc, gs, true);
+            if (stage == 2) return run_stage(ctx, phi->buf1, phi, phi->buf2, nullptr, BASE_RK3_S2, 0.25 * dt, 0, terms, nterms, tc + dt, gs, true);
+            if (stage == 3) return run_stage(ctx, phi->buf2, phi, phi, nullptr, BASE_RK3_S3, (2.0 / 3.0) * dt, 0, terms, nterms, tc + 0.5 * dt, gs, true);
+            return fail(LSM_ERR_ARG, "RK3 has 3 stages");
+        default: return fail(LSM_ERR_ARG, "bad integrator %d", integ);
+    }
+}
+
+int nstages(int integ) { return integ == LSM_FORWARD_EULER ? 1 : integ == LSM_RK2 ? 2 : 3; }
+
+// max over owned nodes of the CFL quantity of one term, as IEEE bits (see lsm_generic.cu K3)
+int32_t cfl_bits(lsm_ctx* ctx, lsm_field* phi, const lsm_term& t, double g, unsigned long long* bits_out) {
+    TermDev td;
+    TRY(make_term_dev(phi, t, g, &td));
+    if (ctx->opt_cfl_cache && t.coef_kind == LSM_COEF_FIELD) {
+        for (const auto& e : ctx->cfl_cache)
+            if (e.kind == t.kind && e.field == t.field && e.version == t.field->version && e.scaled == td.scaled &&
+                (!td.scaled || e.g == g)) { *bits_out = e.bits; return LSM_OK; }
+    }
+    CflParams P{};
+    P.term = td;
+    for (int d = 0; d < 3; ++d) { P.n[d] = phi->n[d]; P.h[d] = phi->h[d]; }
+    P.out = ctx->d_scalar;
+    CU(cudaMemsetAsync(ctx->d_scalar, 0, 8, ctx->stream));
+    cudaError_t e = launch_cfl(phi->ndim, phi->dtype == LSM_F64, P, ctx->sm_count, ctx->stream);
+    if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "CFL kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->cnt.kernel_launches += 1; ctx->cnt.cfl_passes += 1;
+    if (ctx->nranks > 1) NC(nccl().AllReduce(ctx->d_scalar, ctx->d_scalar, 1, ncclUint64, ncclMax, ctx->nccl_comm, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->cnt.d2h_bytes += 8;
+    *bits_out = *ctx->h_scalar;
+    if (ctx->opt_cfl_cache && t.coef_kind == LSM_COEF_FIELD) {
+        bool replaced = false;
+        for (auto& en : ctx->cfl_cache)
+            if (en.kind == t.kind && en.field == t.field) { en = {t.kind, t.field, t.field->version, g, td.scaled, *bits_out}; replaced = true; }
+        if (!replaced) ctx->cfl_cache.push_back({t.kind, t.field, t.field->version, g, td.scaled, *bits_out});
+    }
+    return LSM_OK;
+}
+
+double bits_to_double(unsigned long long b) { double d; std::memcpy(&d, &b, 8); return d; }
+
+// _compute_cfl(term, phi, t) for one term (levelsetterms.jl:30-37 + per-node rules)
+int32_t cfl_term(lsm_ctx* ctx, lsm_field* phi, const lsm_term& t, double g, double* dt_out) {
+    const int N = phi->ndim;
+    double dxmin = phi->h[0];
+    for (int d = 1; d < N; ++d) dxmin = std::min(dxmin, phi->h[d]);
+    const double inf = std::numeric_limits<double>::infinity();
+    if (t.kind == LSM_TERM_EIKONAL) { *dt_out = jl_min(inf, dxmin); return LSM_OK; }    // levelsetterms.jl:250
+    const bool scaled = t.tscale_kind != LSM_TS_NONE;
+    double m;     // max over nodes of sum_d |u_d|/h_d (advection) or of |coefficient| (normal, curvature)
+    if (t.coef_kind == LSM_COEF_CONST) {
+        if (t.kind == LSM_TERM_ADVECTION) {
+            m = 0;
+            for (int d = 0; d < N; ++d) {
+                double v = t.cval[d]; if (scaled) v = v * g;
+                const double q = std::fabs(v) / phi->h[d];
+                m = d == 0 ? q : m + q;
+            }
+        } else {
+            double v = t.cval[0]; if (scaled) v = v * g;
+            m = std::fabs(v);
+        }
+    } else {
+        unsigned long long bits = 0;
+        TRY(cfl_bits(ctx, phi, t, g, &bits));
+        m = bits_to_double(bits);
+    }
+    double r;
+    if (t.kind == LSM_TERM_ADVECTION) r = 1 / m;                                  // levelsetterms.jl:90-96
+    else if (t.kind == LSM_TERM_NORMAL) {                                         // levelsetterms.jl:172-178
+        double s = 0;
+        for (int d = 0; d < N; ++d) { const double q = m / phi->h[d]; s = d == 0 ? q : s + q; }
+        r = 1 / s;
+    } else r = (dxmin * dxmin) / (2 * m);                                         // levelsetterms.jl:123-127
+    *dt_out = jl_min(inf, r);
+    return LSM_OK;
+}
+
+int32_t compute_cfl_impl(lsm_ctx* ctx, lsm_field* phi, const lsm_term* terms, int nterms, double t, const double* gs, double* dt_out) {
+    double dt = std::numeric_limits<double>::infinity();
+    for (int k = 0; k < nterms; ++k) {
+        double d;
+        TRY(cfl_term(ctx, phi, terms[k], term_scale(terms[k], t, gs, k), &d));
+        dt = k == 0 ? d : jl_min(dt, d);
+    }
+    *dt_out = dt;
+    if (!(dt > 0)) return fail(LSM_ERR_CFL, "invalid time-step based on CFL condition: dt = %g (check for NaN/Inf in velocity or speed)", dt);
+    return LSM_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int32_t lsm_abi_version(void) { return LSM_ABI_VERSION; }
+const char* lsm_last_error(void) { return g_err.c_str(); }
+
+int32_t lsm_device_count(int32_t* n_out) {
+    if (!n_out) return fail(LSM_ERR_ARG, "null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *n_out = 0; return fail(LSM_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *n_out = n;
+    return LSM_OK;
+}
+
+int32_t lsm_ctx_create(int32_t device, lsm_ctx** out) {
+    if (!out) return fail(LSM_ERR_ARG, "null argument");
+    lsm_ctx* c = new (std::nothrow) lsm_ctx();
+    if (!c) return fail(LSM_ERR_OOM, "host allocation failed");
+    c->device = device;
+    int32_t rc = ctx_common_init(c);
+    if (rc != LSM_OK) { delete c; return rc; }
+    *out = c;
+    return LSM_OK;
+}
+
+int32_t lsm_nccl_unique_id(void* id128) {
+    if (!id128) return fail(LSM_ERR_ARG, "null argument");
+    const char* why = "";
+    if (!nccl().load(&why)) return fail(LSM_ERR_NCCL, "cannot load NCCL: %s", why);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NC(nccl().GetUniqueId(&id));
+    std::memcpy(id128, &id, 128);
+    return LSM_OK;
+}
+
+int32_t lsm_ctx_create_rank(int32_t device, int32_t rank, int32_t nranks, const void* id128, lsm_ctx** out) {
+    if (!out) return fail(LSM_ERR_ARG, "null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(LSM_ERR_ARG, "bad rank %d of %d", rank, nranks);
+    if (nranks == 1) return lsm_ctx_create(device, out);
+    if (!id128) return fail(LSM_ERR_ARG, "null NCCL id");
+    const char* why = "";
+    if (!nccl().load(&why)) return fail(LSM_ERR_NCCL, "cannot load NCCL: %s", why);
+    lsm_ctx* c = new (std::nothrow) lsm_ctx();
+    if (!c) return fail(LSM_ERR_OOM, "host allocation failed");
+    c->device = device; c->rank = rank; c->nranks = nranks;
+    int32_t rc = ctx_common_init(c);
+    if (rc != LSM_OK) { delete c; return rc; }
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    ncclResult_t r = nccl().CommInitRank(&c->nccl_comm, nranks, id, rank);
+    if (r != ncclSuccess) { delete c; return fail(LSM_ERR_NCCL, "ncclCommInitRank failed: %s", nccl().GetErrorString(r)); }
+    *out = c;
+    return LSM_OK;
+}
+
+int32_t lsm_ctx_destroy(lsm_ctx* c) {
+    if (!c) return LSM_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    resolve_timings(c);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->nccl_comm) nccl().CommDestroy(c->nccl_comm);
+    if (c->d_scalar) cudaFree(c->d_scalar);
+    if (c->h_scalar) cudaFreeHost(c->h_scalar);
+    if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
+    if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->comm) cudaStreamDestroy(c->comm);
+    delete c;
+    return LSM_OK;
+}
+
+int32_t lsm_sync(lsm_ctx* c) {
+    if (!c) return fail(LSM_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->comm));
+    CU(cudaStreamSynchronize(c->stream));
+    return LSM_OK;
+}
+
+int32_t lsm_set_option(lsm_ctx* c, int32_t option, int32_t value) {
+    if (!c) return fail(LSM_ERR_ARG, "null context");
+    switch (option) {
+        case LSM_OPT_KERNEL: if (value < 0 || value > 2) return fail(LSM_ERR_ARG, "LSM_OPT_KERNEL takes 0, 1 or 2"); c->opt_kernel = value; break;
+        case LSM_OPT_TIME_STAGES: c->opt_time = value != 0; break;
+        case LSM_OPT_CFL_CACHE: c->opt_cfl_cache = value != 0; c->cfl_cache.clear(); break;
+        case LSM_OPT_OVERLAP: c->opt_overlap = value != 0; break;
+        default: return fail(LSM_ERR_ARG, "unknown option %d", option);
+    }
+    return LSM_OK;
+}
+
+int32_t lsm_get_counters(lsm_ctx* c, lsm_counters* out) {
+    if (!c || !out) return fail(LSM_ERR_ARG, "null argument");
+    resolve_timings(c);
+    *out = c->cnt;
+    return LSM_OK;
+}
+
+int32_t lsm_reset_counters(lsm_ctx* c) {
+    if (!c) return fail(LSM_ERR_ARG, "null context");
+    resolve_timings(c);
+    c->cnt = lsm_counters{};
+    return LSM_OK;
+}
+
+int32_t lsm_host_register(void* ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return fail(LSM_ERR_ARG, "bad host range");
+    CU(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return LSM_OK;
+}
+int32_t lsm_host_unregister(void* ptr) {
+    if (!ptr) return fail(LSM_ERR_ARG, "null pointer");
+    CU(cudaHostUnregister(ptr));
+    return LSM_OK;
+}
+
+int32_t lsm_slab_plan(int32_t n_last, int32_t nranks, int32_t rank, int32_t* first_out, int32_t* count_out) {
+    if (!first_out || !count_out || nranks < 1 || rank < 0 || rank >= nranks || n_last < 1) return fail(LSM_ERR_ARG, "bad slab plan arguments");
+    int f, c;
+    slab_plan(n_last, nranks, rank, &f, &c);
+    *first_out = f; *count_out = c;
+    return LSM_OK;
+}
+
+int32_t lsm_field_create(lsm_ctx* ctx, int32_t ndim, const int32_t* n, int32_t dtype, int32_t ncomp,
+                         const double* lc, const double* hc, lsm_field** out) {
+    if (!ctx) return fail(LSM_ERR_ARG, "null context");
+    CU(cudaSetDevice(ctx->device));
+    return field_alloc(ctx, ndim, n, dtype, ncomp, lc, hc, true, out);
+}
+
+int32_t lsm_field_create_separable(lsm_ctx* ctx, int32_t ndim, const int32_t* n, const double* lc, const double* hc,
+                                   const double* scale, const double* tabs, lsm_field** out) {
+    if (!ctx || !n || !scale || !tabs || !out) return fail(LSM_ERR_ARG, "null argument");
+    if (ndim < 1 || ndim > 3) return fail(LSM_ERR_ARG, "ndim must be 1, 2 or 3");
+    CU(cudaSetDevice(ctx->device));
+    lsm_field* f = new (std::nothrow) lsm_field();
+    if (!f) return fail(LSM_ERR_OOM, "host allocation failed");
+    f->ctx = ctx; f->ndim = ndim; f->dtype = LSM_F64; f->ncomp = ndim; f->separable = true;
+    long tot = 0;
+    for (int d = 0; d < 3; ++d) {
+        f->nglob[d] = d < ndim ? n[d] : 1; f->n[d] = f->nglob[d];
+        f->lc[d] = (d < ndim && lc) ? lc[d] : 0; f->hc[d] = (d < ndim && hc) ? hc[d] : 1;
+        f->h[d] = d < ndim ? (f->hc[d] - f->lc[d]) / double(f->nglob[d] - 1) : 1.0;
+        f->scale[d] = d < ndim ? scale[d] : 0.0;
+        if (d < ndim) tot += n[d];
+    }
+    const int last = ndim - 1;
+    int first = 0, count = f->nglob[last];
+    if (ctx->nranks > 1) slab_plan(f->nglob[last], ctx->nranks, ctx->rank, &first, &count);
+    f->first_last = first; f->n[last] = count;
+    const size_t bytes = (size_t)tot * ndim * sizeof(double);
+    cudaError_t e = cudaMalloc(&f->d_tabs, bytes);
+    if (e != cudaSuccess) { delete f; return fail(LSM_ERR_OOM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    e = cudaMemcpy(f->d_tabs, tabs, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(f->d_tabs); delete f; return fail(LSM_ERR_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e)); }
+    ctx->cnt.h2d_bytes += (int64_t)bytes;
+    long off = 0;
+    for (int d = 0; d < ndim; ++d)
+        for (int a = 0; a < ndim; ++a) {
+            f->tab[d][a] = f->d_tabs + off + (a == last ? first : 0);
+            off += n[a];
+        }
+    *out = f;
+    return LSM_OK;
+}
+
+int32_t lsm_field_destroy(lsm_field* f) {
+    if (!f) return LSM_OK;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    cudaStreamSynchronize(f->ctx->comm);
+    // drop CFL cache entries that point at this field
+    auto& cc = f->ctx->cfl_cache;
+    for (size_t i = 0; i < cc.size();) { if (cc[i].field == f) cc.erase(cc.begin() + i); else ++i; }
+    field_free(f);
+    return LSM_OK;
+}
+
+int32_t lsm_field_set_bc(lsm_field* f, const lsm_bc* bc) {
+    if (!f || !bc) return fail(LSM_ERR_ARG, "null argument");
+    for (int d = 0; d < f->ndim; ++d) {
+        const lsm_bc l = bc[2 * d], r = bc[2 * d + 1];
+        for (const lsm_bc& b : {l, r}) {
+            if (b.kind < LSM_BC_PERIODIC || b.kind > LSM_BC_SYMMETRY) return fail(LSM_ERR_BC, "invalid boundary condition kind %d for dimension %d", b.kind, d + 1);
+            if (b.kind == LSM_BC_EXTRAP && (b.P < 0 || b.P > LSM_MAX_EXTRAP_P)) return fail(LSM_ERR_BC, "extrapolation order P must be in 0..%d", LSM_MAX_EXTRAP_P);
+        }
+        if ((l.kind == LSM_BC_PERIODIC) != (r.kind == LSM_BC_PERIODIC))     // boundaryconditions.jl:184-186
+            return fail(LSM_ERR_BC, "periodic boundary conditions cannot be mixed with others in dimension %d", d + 1);
+    }
+    for (int d = 0; d < f->ndim; ++d) { f->bc[d][0] = bc[2 * d]; f->bc[d][1] = bc[2 * d + 1]; }
+    f->has_bc = true;
+    f->halo_valid = false;
+    for (lsm_field* b : {f->buf1, f->buf2}) if (b) { std::memcpy(b->bc, f->bc, sizeof f->bc); b->has_bc = true; b->halo_valid = false; }
+    return LSM_OK;
+}
+
+int32_t lsm_field_local_extent(const lsm_field* f, int32_t* n_local, int32_t* first_last) {
+    if (!f || !n_local) return fail(LSM_ERR_ARG, "null argument");
+    for (int d = 0; d < f->ndim; ++d) n_local[d] = f->n[d];
+    if (first_last) *first_last = f->first_last;
+    return LSM_OK;
+}
+
+int32_t lsm_field_meshsize(const lsm_field* f, double* h_out) {
+    if (!f || !h_out) return fail(LSM_ERR_ARG, "null argument");
+    for (int d = 0; d < f->ndim; ++d) h_out[d] = f->h[d];
+    return LSM_OK;
+}
+
+int32_t lsm_field_getindex(lsm_field* f, const int32_t* I, int32_t count, double* out) {
+    if (!f || !I || !out || count < 1) return fail(LSM_ERR_ARG, "bad argument");
+    if (f->separable || f->ncomp != 1) return fail(LSM_ERR_ARG, "getindex needs a scalar dense field");
+    lsm_ctx* c = f->ctx;
+    if (c->nranks > 1) return fail(LSM_ERR_UNSUPPORTED, "lsm_field_getindex is single-rank only");
+    CU(cudaSetDevice(c->device));
+    // in-grid reads need no BC; out-of-grid reads without BCs throw in the reference (meshfield.jl:222-232)
+    for (int t = 0; t < count; ++t)
+        for (int d = 0; d < f->ndim; ++d)
+            if ((I[t * f->ndim + d] < 1 || I[t * f->ndim + d] > f->n[d]) && !f->has_bc)
+                return fail(LSM_ERR_BC, "index lies outside the grid, but the field has no boundary conditions to resolve it");
+    int* d_idx = nullptr; double* d_out = nullptr;
+    CU(cudaMalloc(&d_idx, sizeof(int) * (size_t)count * f->ndim));
+    cudaError_t e = cudaMalloc(&d_out, sizeof(double) * (size_t)count);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, I, sizeof(int) * (size_t)count * f->ndim, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = f->dtype == LSM_F64 ? launch_getindex<double>(f->ndim, make_view<double>(f), d_idx, count, d_out, c->stream)
+                                                  : launch_getindex<float>(f->ndim, make_view<float>(f), d_idx, count, d_out, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_idx); if (d_out) cudaFree(d_out);
+    if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "getindex failed: %s", cudaGetErrorString(e));
+    c->cnt.kernel_launches += 1;
+    return LSM_OK;
+}
+
+int32_t lsm_field_stage_buffer(lsm_field* phi, int32_t which, lsm_field** out) {
+    if (!phi || !out || (which != 1 && which != 2)) return fail(LSM_ERR_ARG, "bad argument");
+    if (phi->ncomp != 1 || phi->separable) return fail(LSM_ERR_ARG, "not a state field");
+    CU(cudaSetDevice(phi->ctx->device));
+    TRY(ensure_buffers(phi, which));
+    *out = which == 1 ? phi->buf1 : phi->buf2;
+    return LSM_OK;
+}
+
+int32_t lsm_field_upload(lsm_field* f, const void* host) {
+    if (!f || !host) return fail(LSM_ERR_ARG, "null argument");
+    if (f->separable) return fail(LSM_ERR_ARG, "separable fields have no dense storage");
+    lsm_ctx* c = f->ctx;
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)f->owned * f->ncomp * esize(f->dtype);
+    if (f->ncomp == 1) {
+        CU(cudaMemcpyAsync(f->p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        void* stage = nullptr;
+        CU(cudaMalloc(&stage, bytes));
+        cudaError_t e = cudaMemcpyAsync(stage, host, bytes, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = launch_transpose(f->dtype == LSM_F64, true, stage, f->p, f->owned, f->ncomp, f->cstride, c->stream);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(stage);
+        if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+        c->cnt.kernel_launches += 1;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->cnt.h2d_bytes += (int64_t)bytes;
+    f->version++; f->halo_valid = false;
+    return LSM_OK;
+}
+
+int32_t lsm_field_download(lsm_field* f, void* host) {
+    if (!f || !host) return fail(LSM_ERR_ARG, "null argument");
+    if (f->separable) return fail(LSM_ERR_ARG, "separable fields have no dense storage");
+    lsm_ctx* c = f->ctx;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->comm));
+    const size_t bytes = (size_t)f->owned * f->ncomp * esize(f->dtype);
+    if (f->ncomp == 1) {
+        CU(cudaMemcpyAsync(host, f->p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        void* stage = nullptr;
+        CU(cudaMalloc(&stage, bytes));
+        cudaError_t e = launch_transpose(f->dtype == LSM_F64, false, f->p, stage, f->owned, f->ncomp, f->cstride, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host, stage, bytes, cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(stage);
+        if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "download failed: %s", cudaGetErrorString(e));
+        c->cnt.kernel_launches += 1;
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->cnt.d2h_bytes += (int64_t)bytes;
+    return LSM_OK;
+}
+
+int32_t lsm_field_copy(lsm_field* dst, const lsm_field* src) {
+    if (!dst || !src) return fail(LSM_ERR_ARG, "null argument");
+    if (dst->separable || src->separable) return fail(LSM_ERR_ARG, "separable fields cannot be copied");
+    if (dst->ctx != src->ctx || dst->ndim != src->ndim || dst->dtype != src->dtype || dst->ncomp != src->ncomp)
+        return fail(LSM_ERR_ARG, "copy between incompatible fields");
+    for (int d = 0; d < dst->ndim; ++d) if (dst->nglob[d] != src->nglob[d]) return fail(LSM_ERR_ARG, "copy between fields of different shape");
+    lsm_ctx* c = dst->ctx;
+    CU(cudaSetDevice(c->device));
+    for (int k = 0; k < dst->ncomp; ++k) {
+        const char* s = static_cast<const char*>(src->p) + (size_t)k * src->cstride * esize(src->dtype);
+        char* d = static_cast<char*>(dst->p) + (size_t)k * dst->cstride * esize(dst->dtype);
+        CU(cudaMemcpyAsync(d, s, (size_t)dst->owned * esize(dst->dtype), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    dst->version++; dst->halo_valid = false;
+    return LSM_OK;
+}
+
+int32_t lsm_compute_cfl(lsm_ctx* ctx, lsm_field* phi, const lsm_term* terms, int32_t nterms, double t,
+                        const double* gscale, double* dt_out) {
+    if (!dt_out) return fail(LSM_ERR_ARG, "null argument");
+    TRY(check_state(ctx, phi, terms, nterms));
+    return compute_cfl_impl(ctx, phi, terms, nterms, t, gscale, dt_out);
+}
+
+int32_t lsm_nstages(int32_t integrator) { return nstages(integrator); }
+
+int32_t lsm_stage(lsm_ctx* ctx, int32_t integrator, int32_t stage, lsm_field* phi, const lsm_term* terms,
+                  int32_t nterms, double tc, double dt, const double* gscale) {
+    TRY(check_state(ctx, phi, terms, nterms));
+    return stage_impl(ctx, integrator, stage, phi, terms, nterms, tc, dt, gscale);
+}
+
+int32_t lsm_advance(lsm_ctx* ctx, int32_t integrator, lsm_field* phi, const lsm_term* terms, int32_t nterms,
+                    double tc, double dt) {
+    TRY(check_state(ctx, phi, terms, nterms));
+    if (integrator < LSM_FORWARD_EULER || integrator > LSM_RK3) return fail(LSM_ERR_ARG, "bad integrator %d", integrator);
+    for (int s = 1; s <= nstages(integrator); ++s) TRY(stage_impl(ctx, integrator, s, phi, terms, nterms, tc, dt, nullptr));
+    return LSM_OK;
+}
+
+int32_t lsm_integrate(lsm_ctx* ctx, int32_t integrator, double cfl, lsm_field* phi, const lsm_term* terms,
+                      int32_t nterms, double t0, double tf, double dt_max, int64_t max_steps,
+                      double* t_out, int64_t* steps_out) {
+    TRY(check_state(ctx, phi, terms, nterms));
+    if (integrator < LSM_FORWARD_EULER || integrator > LSM_RK3) return fail(LSM_ERR_ARG, "bad integrator %d", integrator);
+    if (!(tf >= t0))     // levelsetequation.jl:196
+        return fail(LSM_ERR_TIME, "final time %g must be >= initial time %g: the level-set equation cannot be solved back in time", tf, t0);
+    double tc = t0;
+    int64_t steps = 0;
+    bool finished = true;
+    int32_t rc = LSM_OK;
+    while (tc <= tf - jl_eps(tc)) {                                   // timestepping.jl:104
+        if (max_steps >= 0 && steps >= max_steps) { finished = false; break; }
+        double dt_cfl;
+        rc = compute_cfl_impl(ctx, phi, terms, nterms, tc, nullptr, &dt_cfl);
+        if (rc != LSM_OK) { finished = false; break; }
+        const double dt = jl_min(jl_min(dt_max, cfl * dt_cfl), tf - tc);   // timestepping.jl:111
+        for (int s = 1; s <= nstages(integrator) && rc == LSM_OK; ++s)
+            rc = stage_impl(ctx, integrator, s, phi, terms, nterms, tc, dt, nullptr);
+        if (rc != LSM_OK) { finished = false; break; }
+        tc += dt;
+        ++steps;
+    }
+    cudaStreamSynchronize(ctx->comm);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (t_out) *t_out = finished ? tf : tc;                           // timestepping.jl:120
+    if (steps_out) *steps_out = steps;
+    if (rc != LSM_OK) return rc;
+    if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "device error during integration: %s", cudaGetErrorString(e));
+    return LSM_OK;
+}
+
+int32_t lsm_eikonal_s0(lsm_field* dst, const lsm_field* phi0) {
+    if (!dst || !phi0) return fail(LSM_ERR_ARG, "null argument");
+    if (dst->ctx != phi0->ctx || dst->ndim != phi0->ndim || dst->ncomp != 1 || phi0->ncomp != 1 || dst->separable || phi0->separable)
+        return fail(LSM_ERR_ARG, "incompatible fields");
+    for (int d = 0; d < dst->ndim; ++d) if (dst->nglob[d] != phi0->nglob[d]) return fail(LSM_ERR_ARG, "shape mismatch");
+    lsm_ctx* c = dst->ctx;
+    CU(cudaSetDevice(c->device));
+    double dx = phi0->h[0];
+    for (int d = 1; d < phi0->ndim; ++d) dx = std::min(dx, phi0->h[d]);
+    cudaError_t e = launch_eikonal_s0(phi0->dtype == LSM_F64, dst->dtype == LSM_F64, phi0->p, dst->p, phi0->owned, dx, c->stream);
+    if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    c->cnt.kernel_launches += 1;
+    dst->version++; dst->halo_valid = false;
+    return LSM_OK;
+}
+
+int32_t lsm_max_abs_diff(lsm_ctx* ctx, const lsm_field* a, const lsm_field* b, double* out) {
+    if (!ctx || !a || !b || !out) return fail(LSM_ERR_ARG, "null argument");
+    if (a->ctx != ctx || b->ctx != ctx || a->dtype != b->dtype || a->ncomp != 1 || b->ncomp != 1 || a->owned != b->owned)
+        return fail(LSM_ERR_ARG, "incompatible fields");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->comm));
+    CU(cudaMemsetAsync(ctx->d_scalar, 0, 8, ctx->stream));
+    cudaError_t e = launch_max_abs_diff(a->dtype == LSM_F64, a->p, b->p, a->owned, ctx->d_scalar, ctx->stream);
+    if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->cnt.kernel_launches += 1;
+    if (ctx->nranks > 1) NC(nccl().AllReduce(ctx->d_scalar, ctx->d_scalar, 1, ncclUint64, ncclMax, ctx->nccl_comm, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->cnt.d2h_bytes += 8;
+    *out = bits_to_double(*ctx->h_scalar);
+    return LSM_OK;
+}
+
+}  // extern "C"

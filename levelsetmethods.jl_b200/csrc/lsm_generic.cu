@@ -1,0 +1,529 @@
+// lsm_generic.cu — the STRICT generic kernels (compiled with -fmad=false).
+//
+// One thread per node, any N in {1,2,3}, any term set, any boundary condition.  Arithmetic is
+// written in the reference's own operation order (true divisions by h, left-to-right sums, one
+// rounding to the storage type per term), so results agree with the CPU oracle to the last
+// bit wherever IEEE arithmetic is all that is involved.  This is the correctness anchor on the
+// device and the path for everything the tiled kernels (lsm_tiled.cu) do not cover.
+//
+// Reference functions restated here (paths relative to the reference repo):
+//   meshfield.jl:213-260 getindex/_getindexbc, boundaryconditions.jl:90-153 bc_stencil,
+//   derivatives.jl:28-175, levelsetops.jl:197-244 curvature, levelsetterms.jl:73-265 terms,
+//   timestepping.jl:128-202 stage combinations.
+#include "lsm_dev.cuh"
+#include "lsm_kernels.h"
+
+namespace lsm {
+
+template <class T> struct EpsV;
+template <> struct EpsV<float>  { static constexpr double v = 1.1920928955078125e-07; };
+template <> struct EpsV<double> { static constexpr double v = 2.220446049250313e-16; };
+
+__device__ __forceinline__ double positive(double x) { return x > 0.0 ? x : 0.0; }
+__device__ __forceinline__ double negative(double x) { return x < 0.0 ? x : 0.0; }
+// levelsetterms.jl:184-187
+__device__ __forceinline__ double limiter(double x, double y) {
+    if (!(x * y > 0.0)) return 0.0;
+    return fabs(x) <= fabs(y) ? x : y;
+}
+// Julia max(): NaN-propagating
+__device__ __forceinline__ double jl_max(double a, double b) {
+    return (isnan(a) || isnan(b)) ? __longlong_as_double(0x7FF8000000000000LL) : (b > a ? b : a);
+}
+
+// boundaryconditions.jl:90-97
+__device__ inline double lagrange_w(int j, int k, int P) {
+    double w = 1.0;
+    for (int m = 0; m <= P; ++m) {
+        if (m == j) continue;
+        w *= double(-k - m) / double(j - m);
+    }
+    return w;
+}
+
+// meshfield.jl:248-260 with bc_stencil inlined.  0-based indices.
+template <int N, class T, int DIM>
+__device__ T read_bc(const View<T>& v, int i0, int i1, int i2) {
+    if constexpr (DIM == 0) {
+        return v.p[(long)i0 + (long)i1 * v.s1 + (long)i2 * v.s2];
+    } else {
+        constexpr int d = DIM - 1;
+        const int i = d == 0 ? i0 : (d == 1 ? i1 : i2);
+        const int n = v.n[d];
+        if (i >= 0 && i < n) return read_bc<N, T, DIM - 1>(v, i0, i1, i2);
+        const BCDev bc = i < 0 ? v.bc[d][0] : v.bc[d][1];
+        if (bc.kind == BC_HALO) return read_bc<N, T, DIM - 1>(v, i0, i1, i2);   // stored ghost plane
+        auto rd = [&](int j) -> T {
+            return read_bc<N, T, DIM - 1>(v, d == 0 ? j : i0, d == 1 ? j : i1, d == 2 ? j : i2);
+        };
+        T acc = T(0);
+        if (bc.kind == BC_PERIODIC) {
+            // boundaryconditions.jl:107-119 (1-based: i<1 -> n-(1-i); i>n -> 1+(i-n)); the reference
+            // re-enters getindex when one wrap is not enough (tiny grids) — same as wrapping again.
+            int j = i;
+            for (int it = 0; it < 64 && (j < 0 || j >= n); ++it) j = j < 0 ? (n - 1) + j : 1 + j - n;
+            if (j < 0 || j >= n) return T(__longlong_as_double(0x7FF8000000000000LL));
+            acc += T(1.0) * rd(j);
+        } else if (bc.kind == BC_EXTRAP) {
+            const int k = i < 0 ? -i : i - (n - 1);
+            const int b = i < 0 ? 0 : n - 1;
+            const int dd = i < 0 ? 1 : -1;
+            for (int j = 0; j <= bc.P; ++j) acc += T(lagrange_w(j, k, bc.P)) * rd(b + dd * j);
+        } else if (bc.kind == BC_SYMMETRY) {
+            int j = i;
+            for (int it = 0; it < 64 && (j < 0 || j >= n); ++it) j = j < 0 ? -j : 2 * (n - 1) - j;
+            if (j < 0 || j >= n) return T(__longlong_as_double(0x7FF8000000000000LL));
+            acc += T(1.0) * rd(j);
+        } else {
+            return T(__longlong_as_double(0x7FF8000000000000LL));   // no BC: the reference throws
+        }
+        return acc;
+    }
+}
+
+template <int N, class T>
+__device__ __noinline__ T getindex_slow(const View<T>& v, int i0, int i1, int i2) {
+    return read_bc<N, T, N>(v, i0, i1, i2);
+}
+
+template <int N, class T>
+struct Reader {
+    const View<T>& v;
+    const T* c;          // centre node
+    int i0, i1, i2;
+    bool interior;       // every stencil read (|offset| <= 3 per dim) is a stored element
+    __device__ __forceinline__ long stride(int d) const { return d == 0 ? 1L : (d == 1 ? v.s1 : v.s2); }
+    __device__ __forceinline__ T at(int d, int o) const {
+        if (interior) return c[(long)o * stride(d)];
+        return getindex_slow<N, T>(v, i0 + (d == 0 ? o : 0), i1 + (d == 1 ? o : 0), i2 + (d == 2 ? o : 0));
+    }
+    __device__ __forceinline__ T at2(int d1, int o1, int d2, int o2) const {
+        if (interior) return c[(long)o1 * stride(d1) + (long)o2 * stride(d2)];
+        return getindex_slow<N, T>(v, i0 + (d1 == 0 ? o1 : 0) + (d2 == 0 ? o2 : 0),
+                                   i1 + (d1 == 1 ? o1 : 0) + (d2 == 1 ? o2 : 0),
+                                   i2 + (d1 == 2 ? o1 : 0) + (d2 == 2 ? o2 : 0));
+    }
+};
+
+// derivatives.jl:28-57 evaluated at I + s*e_d
+template <int N, class T> __device__ __forceinline__ double Dm(const Reader<N, T>& r, int d, int s, double h) {
+    T df = r.at(d, s) - r.at(d, s - 1);
+    return double(df) / h;
+}
+template <int N, class T> __device__ __forceinline__ double Dp(const Reader<N, T>& r, int d, int s, double h) {
+    T df = r.at(d, s + 1) - r.at(d, s);
+    return double(df) / h;
+}
+template <int N, class T> __device__ __forceinline__ double D0(const Reader<N, T>& r, int d, double h) {
+    T df = r.at(d, 1) - r.at(d, -1);
+    return double(df) / (2 * h);
+}
+// derivatives.jl:129-175
+template <int N, class T> __device__ __forceinline__ double D20(const Reader<N, T>& r, int d, double h) {
+    T df = r.at(d, 1) - T(2) * r.at(d, 0) + r.at(d, -1);
+    return double(df) / (h * h);
+}
+template <int N, class T> __device__ __forceinline__ double D2pp(const Reader<N, T>& r, int d, double h) {
+    T df = r.at(d, 0) - T(2) * r.at(d, 1) + r.at(d, 2);
+    return double(df) / (h * h);
+}
+template <int N, class T> __device__ __forceinline__ double D2mm(const Reader<N, T>& r, int d, double h) {
+    T df = r.at(d, -2) - T(2) * r.at(d, -1) + r.at(d, 0);
+    return double(df) / (h * h);
+}
+template <int N, class T>
+__device__ __forceinline__ double D2mixed(const Reader<N, T>& r, int d1, int d2, double h1, double h2) {
+    T a = r.at2(d1, 1, d2, 1) - r.at2(d1, 1, d2, -1);
+    T b = r.at2(d1, -1, d2, 1) - r.at2(d1, -1, d2, -1);
+    return (double(a) / (2 * h2) - double(b) / (2 * h2)) / (2 * h1);
+}
+
+// derivatives.jl:61-81
+__device__ __forceinline__ double weno5_strict(double v1, double v2, double v3, double v4, double v5) {
+    const double c13 = 1.0 / 3.0, c76 = 7.0 / 6.0, c116 = 11.0 / 6.0, c16 = 1.0 / 6.0, c56 = 5.0 / 6.0;
+    const double c1312 = 13.0 / 12.0, c14 = 1.0 / 4.0;
+    double d1 = c13 * v1 - c76 * v2 + c116 * v3;
+    double d2 = -c16 * v2 + c56 * v3 + c13 * v4;
+    double d3 = c13 * v3 + c56 * v4 - c16 * v5;
+    double a, b;
+    a = v1 - 2 * v2 + v3;  b = v1 - 4 * v2 + 3 * v3;
+    double S1 = c1312 * (a * a) + c14 * (b * b);
+    a = v2 - 2 * v3 + v4;  b = v2 - v4;
+    double S2 = c1312 * (a * a) + c14 * (b * b);
+    a = v3 - 2 * v4 + v5;  b = 3 * v3 - 4 * v4 + v5;
+    double S3 = c1312 * (a * a) + c14 * (b * b);
+    double m = jl_max(jl_max(jl_max(jl_max(v1 * v1, v2 * v2), v3 * v3), v4 * v4), v5 * v5);
+    double eps = 1.0e-6 * m + 1.0e-99;
+    double t;
+    t = S1 + eps; double a1 = 0.1 / (t * t);
+    t = S2 + eps; double a2 = 0.6 / (t * t);
+    t = S3 + eps; double a3 = 0.3 / (t * t);
+    double w1 = a1 / (a1 + a2 + a3);
+    double w2 = a2 / (a1 + a2 + a3);
+    double w3 = a3 / (a1 + a2 + a3);
+    return w1 * d1 + w2 * d2 + w3 * d3;
+}
+
+template <class T>
+__device__ __forceinline__ double coef_comp(const TermDev& t, long node, int d, int i0, int i1, int i2, int N) {
+    double v;
+    if (t.coef_kind == COEF_CONST) {
+        v = t.cval[d];
+    } else if (t.coef_kind == COEF_FIELD) {
+        const long l = (long)d * t.cstride + node;
+        v = t.coef_f64 ? static_cast<const double*>(t.coef)[l] : double(static_cast<const T*>(t.coef)[l]);
+    } else if (t.coef_kind == COEF_SEPARABLE) {
+        v = t.cval[d];
+        v = v * t.tab[d][0][i0];
+        if (N > 1) v = v * t.tab[d][1][i1];
+        if (N > 2) v = v * t.tab[d][2][i2];
+    } else {
+        v = 0.0;
+    }
+    if (t.scaled) v = v * t.g;
+    return v;
+}
+
+// levelsetterms.jl:156-170 / 252-265 : second-order ENO one-sided pair along dim d
+template <int N, class T>
+__device__ __forceinline__ void eno2_pair(const Reader<N, T>& r, int d, double h, double& neg, double& pos) {
+    const double d20 = D20(r, d, h);
+    neg = Dm(r, d, 0, h) + (0.5 * h) * limiter(D2mm(r, d, h), d20);
+    pos = Dp(r, d, 0, h) - (0.5 * h) * limiter(D2pp(r, d, h), d20);
+}
+
+// levelsetops.jl:197-205
+template <int N, class T>
+__device__ inline double curvature(const Reader<N, T>& r, const double* h) {
+    double g[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < N; ++d) g[d] = D0(r, d, h[d]);
+    double nrmsq = 0.0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) nrmsq += g[d] * g[d];
+    if (nrmsq < EpsV<T>::v) return 0.0;
+    double H[3][3];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i <= j; ++i) {
+            H[i][j] = (i == j) ? D20(r, i, h[i]) : D2mixed(r, i, j, h[i], h[j]);
+            H[j][i] = H[i][j];
+        }
+    double tr = H[0][0];
+#pragma unroll
+    for (int d = 1; d < N; ++d) tr += H[d][d];
+    double quad = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double w = g[0] * H[0][j];
+#pragma unroll
+        for (int i = 1; i < N; ++i) w += g[i] * H[i][j];
+        quad = (j == 0) ? w * g[j] : quad + w * g[j];
+    }
+    return (tr * nrmsq - quad) / pow(nrmsq, 1.5);
+}
+
+template <int N, class T>
+__device__ inline double godunov_norm(const Reader<N, T>& r, const double* h, bool vpos) {
+    double sa = 0, sb = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+        double A, B;
+        eno2_pair(r, d, h[d], A, B);
+        double a, b;
+        if (vpos) { a = positive(A) * positive(A); b = negative(B) * negative(B); }
+        else      { a = negative(A) * negative(A); b = positive(B) * positive(B); }
+        sa = (d == 0) ? a : sa + a;
+        sb = (d == 0) ? b : sb + b;
+    }
+    return sqrt(sa + sb);
+}
+
+template <int N, class T>
+__device__ inline double compute_term(const Reader<N, T>& r, const TermDev& t, long node, const double* h, double dxmin) {
+    switch (t.kind) {
+        case TERM_ADVECTION: {   // levelsetterms.jl:73-82
+            double s = 0.0;
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                const double v = coef_comp<T>(t, node, d, r.i0, r.i1, r.i2, N);
+                double der;
+                if (t.scheme == SCHEME_WENO5) {
+                    if (v > 0) der = weno5_strict(Dm(r, d, -2, h[d]), Dm(r, d, -1, h[d]), Dm(r, d, 0, h[d]), Dm(r, d, 1, h[d]), Dm(r, d, 2, h[d]));
+                    else       der = weno5_strict(Dp(r, d, 2, h[d]), Dp(r, d, 1, h[d]), Dp(r, d, 0, h[d]), Dp(r, d, -1, h[d]), Dp(r, d, -2, h[d]));
+                } else {
+                    der = (v > 0) ? Dm(r, d, 0, h[d]) : Dp(r, d, 0, h[d]);
+                }
+                const double p = v * der;
+                s = (d == 0) ? p : s + p;
+            }
+            return s;
+        }
+        case TERM_NORMAL: {      // levelsetterms.jl:156-170
+            const double v = coef_comp<T>(t, node, 0, r.i0, r.i1, r.i2, N);
+            double gp = 0, gm = 0;
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                double neg, pos;
+                eno2_pair(r, d, h[d], neg, pos);
+                const double a = positive(neg) * positive(neg) + negative(pos) * negative(pos);
+                const double b = negative(neg) * negative(neg) + positive(pos) * positive(pos);
+                gp = (d == 0) ? a : gp + a;
+                gm = (d == 0) ? b : gm + b;
+            }
+            return positive(v) * sqrt(gp) + negative(v) * sqrt(gm);
+        }
+        case TERM_CURVATURE: {   // levelsetterms.jl:111-121
+            const double kappa = curvature(r, h);
+            const double b = coef_comp<T>(t, node, 0, r.i0, r.i1, r.i2, N);
+            double p2 = 0;
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                const double q = D0(r, d, h[d]);
+                p2 = (d == 0) ? q * q : p2 + q * q;
+            }
+            return b * kappa * sqrt(p2);
+        }
+        default: {               // levelsetterms.jl:234-248
+            if (t.coef_kind == COEF_NONE) {
+                const T p = r.at(0, 0);
+                const double nrm = godunov_norm(r, h, p > T(0));
+                const double den = sqrt(double(T(p * p)) + (nrm * nrm) * (dxmin * dxmin));
+                const double S = (den == 0.0) ? 0.0 : double(p) / den;
+                return S * (nrm - 1);
+            }
+            const double S0 = coef_comp<T>(t, node, 0, r.i0, r.i1, r.i2, N);
+            const double nrm = godunov_norm(r, h, S0 > 0);
+            return S0 * (nrm - 1);
+        }
+    }
+}
+
+template <int N, class T>
+__global__ void __launch_bounds__(256) stage_generic_kernel(const __grid_constant__ StageParams<T> P) {
+    const View<T>& v = P.in;
+    const int n0 = v.n[0], n1 = v.n[1];
+    const int nr = P.r1 - P.r0;
+    const long total = (N == 1) ? (long)nr : (N == 2) ? (long)n0 * nr : (long)n0 * n1 * nr;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int i0, i1 = 0, i2 = 0;
+    if (N == 1) { i0 = P.r0 + (int)idx; }
+    else if (N == 2) { i0 = (int)(idx % n0); i1 = P.r0 + (int)(idx / n0); }
+    else { i0 = (int)(idx % n0); long q = idx / n0; i1 = (int)(q % n1); i2 = P.r0 + (int)(q / n1); }
+
+    const long lin = (long)i0 + (long)i1 * v.s1 + (long)i2 * v.s2;
+    const long node = (long)i0 + (long)n0 * ((long)i1 + (long)n1 * i2);   // coefficient boxes carry no ghosts
+
+    bool interior = true;
+    {
+        const int R = 3;
+        const int ii[3] = {i0, i1, i2};
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            if (ii[d] - R < 0 && v.bc[d][0].kind != BC_HALO) interior = false;
+            if (ii[d] + R >= v.n[d] && v.bc[d][1].kind != BC_HALO) interior = false;
+        }
+    }
+    Reader<N, T> r{v, v.p + lin, i0, i1, i2, interior};
+
+    const T inc = v.p[lin];
+    T x;
+    switch (P.base) {
+        case BASE_IN:     x = inc; break;
+        case BASE_RK3_S2: x = T(0.75 * double(P.p0[lin]) + 0.25 * double(inc)); break;   // timestepping.jl:183
+        case BASE_RK3_S3: x = T((P.p0[lin] + T(2) * inc) / T(3)); break;                  // timestepping.jl:194
+        default:          x = P.p0[lin]; break;
+    }
+    T x2 = inc;
+    for (int k = 0; k < P.nterms; ++k) {
+        const double H = compute_term<N, T>(r, P.terms[k], node, P.h, P.dxmin);
+        x = T(double(x) - P.c * H);
+        if (P.out2) x2 = T(double(x2) - P.c2 * H);
+    }
+    P.out[lin] = x;
+    if (P.out2) P.out2[lin] = x2;
+}
+
+template <class T>
+cudaError_t launch_stage_generic(int ndim, const StageParams<T>& P, cudaStream_t s) {
+    const View<T>& v = P.in;
+    const long nr = P.r1 - P.r0;
+    if (nr <= 0) return cudaSuccess;
+    const long total = ndim == 1 ? nr : ndim == 2 ? (long)v.n[0] * nr : (long)v.n[0] * v.n[1] * nr;
+    const int block = 256;
+    const long grid = (total + block - 1) / block;
+    if (grid > 2147483647L) return cudaErrorInvalidConfiguration;
+    if (ndim == 1) stage_generic_kernel<1, T><<<(unsigned)grid, block, 0, s>>>(P);
+    else if (ndim == 2) stage_generic_kernel<2, T><<<(unsigned)grid, block, 0, s>>>(P);
+    else stage_generic_kernel<3, T><<<(unsigned)grid, block, 0, s>>>(P);
+    return cudaGetLastError();
+}
+template cudaError_t launch_stage_generic<float>(int, const StageParams<float>&, cudaStream_t);
+template cudaError_t launch_stage_generic<double>(int, const StageParams<double>&, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
+// K3: CFL reduction (levelsetterms.jl:22-38, 90-96, 123-127, 172-178).
+// The reference takes min over nodes of 1/sum_d(|u_d|/h_d) (advection), 1/sum_d(|v|/h_d) (normal),
+// dx^2/(2|b|) (curvature).  x -> 1/x and the other two maps are monotone under correct rounding, so
+// the min equals the map applied to the MAX of sum_d(|u_d|/h_d), |v|, |b| — bit for bit.  The
+// kernel reduces that max (warp shuffle + block shared-memory + one atomicMax per block) on the
+// IEEE bit pattern: non-negative doubles order like unsigned integers, and a (sign-cleared) NaN
+// compares above +Inf, so a NaN anywhere wins the max and reaches the host, which then fails
+// `dt > 0` exactly like the reference.
+// ---------------------------------------------------------------------------------------------
+template <int N, class T>
+__global__ void __launch_bounds__(256) cfl_kernel(const __grid_constant__ CflParams P) {
+    const TermDev& t = P.term;
+    const long total = (long)P.n[0] * P.n[1] * P.n[2];
+    unsigned long long best = 0ULL;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i0 = (int)(idx % P.n[0]);
+        const long q = idx / P.n[0];
+        const int i1 = (int)(q % P.n[1]);
+        const int i2 = (int)(q / P.n[1]);
+        double s;
+        if (t.kind == TERM_ADVECTION) {
+            s = 0.0;
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                const double v = coef_comp<T>(t, idx, d, i0, i1, i2, N);
+                const double q2 = fabs(v) / P.h[d];
+                s = (d == 0) ? q2 : s + q2;
+            }
+        } else {
+            s = fabs(coef_comp<T>(t, idx, 0, i0, i1, i2, N));
+        }
+        const unsigned long long bits = isnan(s) ? 0x7FF8000000000000ULL : (unsigned long long)__double_as_longlong(s);
+        best = bits > best ? bits : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    __shared__ unsigned long long wbest[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wbest[w] = best;
+    __syncthreads();
+    if (w == 0) {
+        best = lane < (int)(blockDim.x >> 5) ? wbest[lane] : 0ULL;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if (lane == 0) atomicMax(P.out, best);
+    }
+}
+
+cudaError_t launch_cfl(int ndim, int dtype_f64, const CflParams& P, int sm_count, cudaStream_t s) {
+    const long total = (long)P.n[0] * P.n[1] * P.n[2];
+    const int block = 256;
+    long grid = (total + block - 1) / block;
+    const long cap = (long)sm_count * 8;     // persistent-style: 8 CTAs of 256 threads per SM
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+#define LSM_CFL(NN) do { if (dtype_f64) cfl_kernel<NN, double><<<(unsigned)grid, block, 0, s>>>(P); \
+                         else cfl_kernel<NN, float><<<(unsigned)grid, block, 0, s>>>(P); } while (0)
+    if (ndim == 1) LSM_CFL(1); else if (ndim == 2) LSM_CFL(2); else LSM_CFL(3);
+#undef LSM_CFL
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// small elementwise kernels
+// ---------------------------------------------------------------------------------------------
+// EikonalReinitializationTerm(phi0): S0 = v / sqrt(v^2 + dx^2)   (levelsetterms.jl:217-221)
+template <class T, class TO>
+__global__ void eikonal_s0_kernel(const T* __restrict__ phi, TO* __restrict__ out, long n, double dx) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const T v = phi[i];
+        out[i] = TO(double(v) / sqrt(double(T(v * v)) + dx * dx));
+    }
+}
+
+cudaError_t launch_eikonal_s0(int src_f64, int dst_f64, const void* phi, void* out, long n, double dx, cudaStream_t s) {
+    const int block = 256;
+    long grid = (n + block - 1) / block; if (grid > 148L * 16) grid = 148L * 16; if (grid < 1) grid = 1;
+    if (src_f64 && dst_f64) eikonal_s0_kernel<double, double><<<(unsigned)grid, block, 0, s>>>((const double*)phi, (double*)out, n, dx);
+    else if (src_f64) eikonal_s0_kernel<double, float><<<(unsigned)grid, block, 0, s>>>((const double*)phi, (float*)out, n, dx);
+    else if (dst_f64) eikonal_s0_kernel<float, double><<<(unsigned)grid, block, 0, s>>>((const float*)phi, (double*)out, n, dx);
+    else eikonal_s0_kernel<float, float><<<(unsigned)grid, block, 0, s>>>((const float*)phi, (float*)out, n, dx);
+    return cudaGetLastError();
+}
+
+// AoS (host layout, component fastest) <-> SoA (device layout) for vector coefficient fields
+template <class T>
+__global__ void aos_to_soa_kernel(const T* __restrict__ aos, T* __restrict__ soa, long n, int ncomp, long cstride) {
+    const long tot = n * ncomp;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long)gridDim.x * blockDim.x) {
+        const long node = i / ncomp; const int d = (int)(i % ncomp);
+        soa[(long)d * cstride + node] = aos[i];
+    }
+}
+template <class T>
+__global__ void soa_to_aos_kernel(const T* __restrict__ soa, T* __restrict__ aos, long n, int ncomp, long cstride) {
+    const long tot = n * ncomp;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long)gridDim.x * blockDim.x) {
+        const long node = i / ncomp; const int d = (int)(i % ncomp);
+        aos[i] = soa[(long)d * cstride + node];
+    }
+}
+cudaError_t launch_transpose(int f64, bool to_soa, const void* src, void* dst, long n, int ncomp, long cstride, cudaStream_t s) {
+    const int block = 256;
+    long grid = (n * ncomp + block - 1) / block; if (grid > 148L * 16) grid = 148L * 16; if (grid < 1) grid = 1;
+    if (f64) { if (to_soa) aos_to_soa_kernel<double><<<(unsigned)grid, block, 0, s>>>((const double*)src, (double*)dst, n, ncomp, cstride);
+               else soa_to_aos_kernel<double><<<(unsigned)grid, block, 0, s>>>((const double*)src, (double*)dst, n, ncomp, cstride); }
+    else     { if (to_soa) aos_to_soa_kernel<float><<<(unsigned)grid, block, 0, s>>>((const float*)src, (float*)dst, n, ncomp, cstride);
+               else soa_to_aos_kernel<float><<<(unsigned)grid, block, 0, s>>>((const float*)src, (float*)dst, n, ncomp, cstride); }
+    return cudaGetLastError();
+}
+
+// phi[I] for arbitrary (possibly out-of-grid) 1-based indices: meshfield.jl:213-217
+template <int N, class T>
+__global__ void getindex_kernel(const __grid_constant__ View<T> v, const int* __restrict__ idx, int count, double* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int i0 = idx[t * N] - 1;
+    const int i1 = N > 1 ? idx[t * N + 1] - 1 : 0;
+    const int i2 = N > 2 ? idx[t * N + 2] - 1 : 0;
+    out[t] = double(getindex_slow<N, T>(v, i0, i1, i2));
+}
+template <class T>
+cudaError_t launch_getindex(int ndim, const View<T>& v, const int* d_idx, int count, double* d_out, cudaStream_t s) {
+    const int block = 128, grid = (count + block - 1) / block;
+    if (ndim == 1) getindex_kernel<1, T><<<grid, block, 0, s>>>(v, d_idx, count, d_out);
+    else if (ndim == 2) getindex_kernel<2, T><<<grid, block, 0, s>>>(v, d_idx, count, d_out);
+    else getindex_kernel<3, T><<<grid, block, 0, s>>>(v, d_idx, count, d_out);
+    return cudaGetLastError();
+}
+template cudaError_t launch_getindex<float>(int, const View<float>&, const int*, int, double*, cudaStream_t);
+template cudaError_t launch_getindex<double>(int, const View<double>&, const int*, int, double*, cudaStream_t);
+
+// K6: max |a - b| (bit-pattern max, NaN wins)
+template <class T>
+__global__ void __launch_bounds__(256) max_abs_diff_kernel(const T* __restrict__ a, const T* __restrict__ b, long n, unsigned long long* out) {
+    unsigned long long best = 0ULL;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const double d = fabs(double(a[i]) - double(b[i]));
+        const unsigned long long bits = isnan(d) ? 0x7FF8000000000000ULL : (unsigned long long)__double_as_longlong(d);
+        best = bits > best ? bits : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(out, best);
+}
+cudaError_t launch_max_abs_diff(int f64, const void* a, const void* b, long n, unsigned long long* out, cudaStream_t s) {
+    const int block = 256;
+    long grid = (n + block - 1) / block; if (grid > 148L * 8) grid = 148L * 8; if (grid < 1) grid = 1;
+    if (f64) max_abs_diff_kernel<double><<<(unsigned)grid, block, 0, s>>>((const double*)a, (const double*)b, n, out);
+    else max_abs_diff_kernel<float><<<(unsigned)grid, block, 0, s>>>((const float*)a, (const float*)b, n, out);
+    return cudaGetLastError();
+}
+
+}  // namespace lsm

@@ -1,0 +1,12 @@
+"""Import shim: ``import lsm_b200`` loads the package in ``levelsetmethods.jl_b200/`` (a directory
+name Python cannot import directly) under the module name ``lsm_b200``."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "levelsetmethods.jl_b200")
+_spec = importlib.util.spec_from_file_location("lsm_b200", os.path.join(_dir, "__init__.py"),
+                                               submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["lsm_b200"] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,116 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/lsm_b200.h declares,
+host-side logic (grid, BC normalisation, slab plan) and loud failure without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def m():
+    import lsm_b200
+    return lsm_b200
+
+
+def test_header_symbols_all_exported(m):
+    hdr = open(os.path.join(ROOT, "include", "lsm_b200.h")).read()
+    declared = set(re.findall(r"\b(lsm_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = C.CDLL(m._lib.SO_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(m._lib.SYMBOLS), "ctypes binding and header disagree"
+    assert lib.lsm_abi_version() == 1
+
+
+def test_header_cites_reference(m):
+    hdr = open(os.path.join(ROOT, "include", "lsm_b200.h")).read()
+    for cite in ("timestepping.jl:101-122", "levelsetterms.jl:22-38", "meshfield.jl:213-260", "boundaryconditions.jl:166-188"):
+        assert cite in hdr
+
+
+def test_product_never_touches_oracle():
+    """The oracle is test infrastructure: nothing under the package may import, link or load it."""
+    pkg = os.path.join(ROOT, "levelsetmethods.jl_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "lsm_oracle" not in txt and "import oracle" not in txt and "orc_" not in txt, f
+
+
+def test_no_gpu_fails_loudly(m):
+    lib = m._lib.lib()
+    n = C.c_int32(-1)
+    rc = lib.lsm_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(m.LSMError) as ei:
+        m.Context(0)
+    assert ei.value.code == m._lib.ERR_CUDA
+
+
+def test_slab_plan(m):
+    lib = m._lib.lib()
+    for n, g in ((1024, 8), (512, 3), (130, 4), (7, 7)):
+        covered = []
+        for r in range(g):
+            f, c = C.c_int32(), C.c_int32()
+            assert lib.lsm_slab_plan(n, g, r, C.byref(f), C.byref(c)) == 0
+            covered += list(range(f.value, f.value + c.value))
+            assert abs(c.value - n / g) < 1
+        assert covered == list(range(n))
+    f, c = C.c_int32(), C.c_int32()
+    assert lib.lsm_slab_plan(10, 2, 2, C.byref(f), C.byref(c)) == m._lib.ERR_ARG
+
+
+# ---- test/test-meshes.jl ----
+def test_grid(m):
+    g = m.CartesianGrid((-1, 0), (1, 3), (100, 50))
+    assert g.size == (100, 50) and len(g) == 5000
+    assert g.getnode(1, 1) == (-1.0, 0.0) and g.getnode(100, 50) == (1.0, 3.0)
+    g = m.CartesianGrid((-1, -1), (1, 1), meshsize=0.5)
+    assert g.size == (5, 5) and g.meshsize() == pytest.approx((0.5, 0.5))
+    assert g.getnode(5, 5) == (1.0, 1.0)
+    g = m.CartesianGrid((0, 0), (1, 1), meshsize=0.3)
+    assert g.size == (5, 5) and all(h <= 0.3 for h in g.meshsize())
+    g = m.CartesianGrid((0, 0), (2, 1), meshsize=(0.4, 0.3))
+    assert g.size == (6, 5)
+    for bad in (dict(meshsize=-0.1), dict(meshsize=(0.1,))):
+        with pytest.raises(ValueError):
+            m.CartesianGrid((0, 0), (1, 1), **bad)
+    with pytest.raises(ValueError):
+        m.CartesianGrid((1, 1), (0, 0), meshsize=0.1)
+
+
+# ---- test/test-boundaryconditions.jl ----
+def test_normalize_bc(m):
+    P, N, E = m.PeriodicBC(), m.NeumannBC(), m.ExtrapolationBC(2)
+    assert m._normalize_bc(P, 2) == ((P, P), (P, P))
+    assert m._normalize_bc((P, P), 2) == ((P, P), (P, P))
+    assert m._normalize_bc((P, N), 2) == ((P, P), (N, N))
+    r = m._normalize_bc([P, (E, N)], 2)
+    assert r[0] == (P, P) and r[1] == (E, N)
+    with pytest.raises(ValueError):
+        m._normalize_bc([(P, E), (E, N)], 2)
+    with pytest.raises(ValueError):
+        m.ExtrapolationBC(-1)
+
+
+def test_equation_construction_errors(m):
+    g = m.CartesianGrid((-1, -1), (1, 1), (8, 8))
+    phi = m.MeshField(lambda x: x[0] ** 2 + x[1] ** 2 - 0.25, g)
+    assert phi.vals.shape == (8, 8) and not phi.has_boundary_conditions()
+    with pytest.raises(m.BCError):
+        m.LevelSetEquation(terms=(m.CurvatureTerm(-0.1),), ic=phi)                 # levelsetequation.jl:69-70
+    with pytest.raises(ValueError):
+        m.LevelSetEquation(terms=[m.CurvatureTerm(-0.1)], ic=phi, bc=m.NeumannBC())  # _normalize_terms
+    eq = m.LevelSetEquation(terms=m.CurvatureTerm(-0.1), ic=phi, bc=m.NeumannBC())
+    assert isinstance(eq.integrator, m.RK2) and eq.integrator.cfl == 0.5           # default RK2 (:61)
+    assert eq.state is not phi and np.array_equal(eq.state.peek(), phi.peek())     # ic is copied
+    with pytest.raises(m.TimeError):
+        m.integrate(eq, -1.0)                                                      # levelsetequation.jl:196

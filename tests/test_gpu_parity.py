@@ -1,0 +1,328 @@
+"""GPU parity tests proper: every call goes through the C ABI (liblsm_b200.so) and is compared with
+the CPU oracle on the same seed-free inputs.  Tolerances are the ones BASELINE.json states:
+max-abs phi difference <= 1e-10 (Float64) / <= 1e-4 (Float32) after 100 RK3 steps, identical sign and
+cut-cell classification.  The strict generic kernel is additionally required to match the oracle to
+rounding level (<= 1e-13 relative) on every term / BC / dimension / dtype combination.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+OPT_KERNEL = 0
+
+
+@pytest.fixture(scope="module")
+def m():
+    import lsm_b200
+    return lsm_b200
+
+
+@pytest.fixture()
+def strict(m):
+    ctx = m.default_context()
+    ctx.set_option(OPT_KERNEL, 1)
+    yield ctx
+    ctx.set_option(OPT_KERNEL, 0)
+
+
+INTEG = {"FE": 0, "RK2": 1, "RK3": 2}
+
+
+def run_pair(m, O, case, integ="RK3", steps=100, tf=None, cfl=0.5):
+    """Integrate `case` with the oracle and the engine; return (phi_oracle, phi_engine, t, nsteps)."""
+    fo = case.oracle_field()
+    to = case.oracle_terms()
+    # choose tf from the initial CFL step so that exactly `steps` steps are taken when dt is constant
+    if tf is None:
+        dt0 = cfl * O.compute_cfl(fo, to, 0.0)
+        tf = dt0 * steps * (1 - 1e-12)
+    t_o, n_o = O.integrate(fo, INTEG[integ], to, tf, cfl=cfl)
+    phi = case.engine_field(m)
+    terms = case.engine_terms(m, phi)
+    eq = m.LevelSetEquation(terms=terms, ic=phi, integrator=getattr(m, {"FE": "ForwardEuler"}.get(integ, integ))(cfl))
+    m.integrate(eq, tf)
+    assert eq.t == t_o
+    assert eq.steps_taken == n_o
+    return fo.vals, eq.state.peek(), t_o, n_o
+
+
+def check_parity(a, b, tol):
+    assert not np.isnan(b).any()
+    d = np.abs(a.astype(np.float64) - b.astype(np.float64)).max()
+    assert d <= tol, f"max-abs difference {d:.3e} > {tol:.1e}"
+    assert np.array_equal(np.sign(a), np.sign(b)), "zero-level-set node classification differs"
+    assert np.array_equal(H.cut_cells(a), H.cut_cells(b)), "cut-cell classification differs"
+    return d
+
+
+# ------------------------------------------------------------------------------------------------
+# ghost cells on the device (test/test-meshfield.jl:44-125) against the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_device_getindex_matches_oracle(m, O, dtype):
+    rng = np.random.default_rng(0)
+    bcs = [("periodic",), ("neumann",), ("extrap", 1), ("extrap", 2), ("extrap", 3), ("symmetry",)]
+    for n in [(12,), (10, 7), (8, 6, 7)]:
+        N = len(n)
+        vals = rng.standard_normal(n).astype(dtype)
+        for i, b in enumerate(bcs):
+            bc = tuple(bcs[(i + d) % len(bcs)] if d else b for d in range(N))      # mix kinds across dims
+            case = H.Case("g", [0.0] * N, [1.0] * N, n, vals, [], bc, dtype)
+            fo = case.oracle_field()
+            phi = case.engine_field(m)
+            for _ in range(40):
+                I = tuple(int(rng.integers(-2, n[d] + 4)) for d in range(N))      # 1-based, up to 3 outside
+                assert phi[I] == fo[I], (n, bc, I)
+
+
+def test_device_getindex_reference_cases(m):
+    g = m.CartesianGrid((0, 0), (1, 1), (10, 5))
+    vals = np.random.default_rng(1).random((10, 5))
+    mf = m.MeshField(vals, g, bc=(m.PeriodicBC(), m.PeriodicBC()))
+    assert mf[1, 1] == vals[0, 0] and mf[1, 0] == vals[0, 3] and mf[11, 5] == mf[2, 5]
+    g1 = m.CartesianGrid((0.0,), (4.0,), (5,))
+    s = m.MeshField(lambda x: x[0], g1, bc=m.SymmetryBC())
+    assert (s[0], s[-1], s[6], s[7]) == (1.0, 2.0, 3.0, 2.0)
+    nb = m.MeshField(lambda x: x[0], g1)
+    with pytest.raises(m.BCError):
+        nb[0]                                     # meshfield.jl:222-232: no BC to resolve a ghost
+    a, b, n = -0.3, 1.7, 10
+    h = (b - a) / (n - 1)
+    for P in range(0, 6):
+        for k in range(0, P + 1):
+            f = m.MeshField(lambda x: x[0] ** k, m.CartesianGrid((a,), (b,), (n,)), bc=m.ExtrapolationBC(P))
+            for j in range(1, P + 2):
+                assert f[1 - j] == pytest.approx((a - j * h) ** k, abs=1e-10)
+                assert f[n + j] == pytest.approx((b + j * h) ** k, abs=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------
+# CFL (test/test-levelsetterms.jl:7-31) : bit-exact against the oracle
+# ------------------------------------------------------------------------------------------------
+def test_cfl_bitexact_and_errors(m, O):
+    for case in (H.c1_circle_rotation(64), H.c3_enright(24), H.c5_normal_advection(24), H.c2_zalesak_curvature(64),
+                 H.c3_enright(24, separable=True), H.c1_circle_rotation(48, np.float32)):
+        fo, to = case.oracle_field(), case.oracle_terms()
+        phi = case.engine_field(m)
+        terms = case.engine_terms(m, phi)
+        for t in (0.0, 0.37, 1.4):
+            assert m.compute_cfl(terms, phi, t) == O.compute_cfl(fo, to, t), case.name
+    g = m.CartesianGrid((-1.0,), (1.0,), (100,))
+    phi = m.MeshField(lambda x: x[0], g, bc=m.NeumannBC())
+    dx = g.meshsize(1)
+    assert m.compute_cfl((m.AdvectionTerm(lambda x, t: (2.0,)),), phi, 0.0) == pytest.approx(dx / 2.0, rel=1e-15)
+    assert m.compute_cfl((m.NormalMotionTerm(lambda x, t: 3.0),), phi, 0.0) == pytest.approx(dx / 3.0, rel=1e-15)
+    assert m.compute_cfl((m.AdvectionTerm((0.0,)),), phi, 0.0) == math.inf
+    u = np.ones((1, 100)); u[0, 17] = np.nan
+    with pytest.raises(m.CFLError):
+        m.compute_cfl((m.AdvectionTerm(m.MeshField(u, g)),), phi, 0.0)
+    u[0, 17] = np.inf
+    with pytest.raises(m.CFLError):
+        m.compute_cfl((m.AdvectionTerm(m.MeshField(u, g)),), phi, 0.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# strict kernel: every term x BC x dim x dtype x integrator, a few steps, rounding-level agreement
+# ------------------------------------------------------------------------------------------------
+def _small_cases():
+    out = []
+    rng = np.random.default_rng(3)
+    for N, n in ((1, (40,)), (2, (26, 22)), (3, (14, 12, 13))):
+        lc, hc = [-1.0] * N, [1.0 + 0.1 * d for d in range(N)]
+        X = H.coords(lc, hc, n)
+        r = np.sqrt(sum((x - 0.1) ** 2 for x in X))
+        phi = H.bcast((r - 0.5) * (1 + 0.3 * np.sin(3 * X[0])), n)
+        u = np.stack([H.bcast(np.sin(2 * X[d] + d) + 0.2, n) for d in range(N)], axis=0)
+        v = H.bcast(0.3 + 0.5 * np.cos(2 * X[0]), n)
+        b = H.bcast(-0.02 - 0.01 * np.sin(X[-1]), n)
+        bcs = [("periodic",), ("neumann",), ("extrap", 2), ("symmetry",), ("extrap", 1)]
+        termsets = {
+            "adv_weno": [dict(kind="advection", field=u)],
+            "adv_upwind": [dict(kind="advection", field=u, scheme="upwind")],
+            "adv_const_cos": [dict(kind="advection", const=tuple([0.7, -0.4, 0.5][:N]), cos_period=0.05)],
+            "normal": [dict(kind="normal", field=v)],
+            "normal_const": [dict(kind="normal", const=-0.8)],
+            "curv": [dict(kind="curvature", field=b)],
+            "curv_const": [dict(kind="curvature", const=-0.05)],
+            "eik_frozen": [dict(kind="eikonal", frozen=True)],
+            "eik_live": [dict(kind="eikonal", frozen=False)],
+            "three": [dict(kind="normal", field=v), dict(kind="advection", field=u), dict(kind="curvature", const=-0.01)],
+        }
+        for i, (tn, ts) in enumerate(termsets.items()):
+            bc = tuple(bcs[(i + d) % len(bcs)] for d in range(N))
+            if N > 1 and i % 3 == 0:
+                bc = (bc[0],) + ((("neumann",), ("extrap", 1)),) + bc[2:]       # different left / right
+            out.append((f"{N}d-{tn}", H.Case(tn, lc, hc, n, phi, ts, bc)))
+    return out
+
+
+@pytest.mark.parametrize("name,case", _small_cases(), ids=[c[0] for c in _small_cases()])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_strict_kernel_all_terms(m, O, strict, name, case, dtype):
+    case = H.Case(case.name, case.lc, case.hc, case.n, case.phi0, case.terms, case.bc, dtype)
+    for integ in ("FE", "RK2", "RK3"):
+        a, b, _, n = run_pair(m, O, case, integ=integ, steps=4)
+        assert n == 4 or "cos" in name
+        tol = 1e-13 if dtype == np.float64 else 2e-6
+        d = np.abs(a.astype(np.float64) - b.astype(np.float64)).max()
+        assert d <= tol * max(1.0, np.abs(a).max()), (name, integ, d)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs, 100 RK3 steps, default kernel selection (tiled where available)
+# ------------------------------------------------------------------------------------------------
+CONFIGS = [
+    ("C1-128", lambda dt: H.c1_circle_rotation(128, dt)),
+    ("C2-192", lambda dt: H.c2_zalesak_curvature(192, dt)),
+    ("C3-48", lambda dt: H.c3_enright(48, dt)),
+    ("C3sep-48", lambda dt: H.c3_enright(48, dt, separable=True)),
+    ("C4-48", lambda dt: H.c4_eikonal(48, dt)),
+    ("C5-48", lambda dt: H.c5_normal_advection(48, dt)),
+]
+
+
+@pytest.mark.parametrize("name,mk", CONFIGS, ids=[c[0] for c in CONFIGS])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_config_parity_100_steps(m, O, name, mk, dtype):
+    case = mk(dtype)
+    steps = 50 if name.startswith("C4") else 100
+    a, b, t, n = run_pair(m, O, case, integ="RK3", steps=steps)
+    assert n >= 0.9 * steps
+    d = check_parity(a, b, 1e-10 if dtype == np.float64 else 1e-4)
+    print(f"{name} {np.dtype(dtype).name}: {n} steps, max-abs diff {d:.3e}")
+
+
+def test_c4_rk2_reference_default(m, O):
+    a, b, _, n = run_pair(m, O, H.c4_eikonal(40), integ="RK2", steps=50)
+    check_parity(a, b, 1e-10)
+
+
+def test_strict_and_default_kernels_agree(m, O, strict):
+    """Same run through the strict generic kernel: must also be inside the tolerance (and is in fact at rounding level)."""
+    a, b, _, _ = run_pair(m, O, H.c3_enright(40), steps=60)
+    d = check_parity(a, b, 1e-10)
+    assert d <= 1e-13
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own integration tests, run through the engine (test-timestepping.jl, test-levelsetequation.jl)
+# ------------------------------------------------------------------------------------------------
+def _adv_err_1d(m, integ, N, u=1.0, tf=0.5, scheme=None):
+    g = m.CartesianGrid((-1.0,), (1.0,), (N,))
+    phi = m.MeshField(lambda x: np.sin(np.pi * x[0]), g)
+    term = m.AdvectionTerm(lambda x, t: (u,), scheme or m.WENO5())
+    eq = m.LevelSetEquation(terms=(term,), ic=phi, bc=m.PeriodicBC(), integrator=integ)
+    m.integrate(eq, tf)
+    x = g.coords()[0]
+    return np.abs(eq.state.peek() - np.sin(np.pi * (x - u * tf))).max()
+
+
+def test_reference_timestepping_tests(m):
+    assert _adv_err_1d(m, m.ForwardEuler(), 200) < 0.05
+    assert _adv_err_1d(m, m.RK2(), 200) < 1.0e-3
+    assert _adv_err_1d(m, m.RK3(), 200) < 1.0e-5
+    Ns = [50, 100, 200, 400]
+    for mk, p in ((m.ForwardEuler, 1), (m.RK2, 2), (m.RK3, 3)):
+        e = [_adv_err_1d(m, mk(), N) for N in Ns]
+        for i in range(len(Ns) - 1):
+            assert math.log(e[i] / e[i + 1]) / math.log(Ns[i + 1] / Ns[i]) >= p - 0.5
+
+
+def test_reference_spatial_orders(m):
+    e = [_adv_err_1d(m, m.RK3(1e-2), N) for N in (20, 40, 80)]
+    assert all(math.log(e[i] / e[i + 1]) / math.log(2) >= 4.5 for i in range(2))
+    e = [_adv_err_1d(m, m.RK3(1e-2), N, scheme=m.Upwind()) for N in (50, 100, 200)]
+    assert all(math.log(e[i] / e[i + 1]) / math.log(2) >= 0.8 for i in range(2))
+
+
+def test_reference_normal_and_curvature_orders(m):
+    def run(N, term, exact, r0):
+        g = m.CartesianGrid((-2.0, -2.0), (2.0, 2.0), (N, N))
+        phi = m.MeshField(lambda x: np.sqrt(x[0] ** 2 + x[1] ** 2) - r0, g)
+        eq = m.LevelSetEquation(terms=(term,), ic=phi, bc=m.ExtrapolationBC(2), integrator=m.RK3())
+        m.integrate(eq, 0.2)
+        x, y = g.coords()
+        r = np.sqrt(x * x + y * y)
+        return np.where((r >= 0.5) & (r <= 1.5), np.abs(eq.state.peek() - exact(r)), 0.0).max()
+
+    e = [run(N, m.NormalMotionTerm(lambda x, t: 0.5), lambda r: r - 0.5 - 0.5 * 0.2, 0.5) for N in (30, 60, 120)]
+    assert all(math.log(e[i] / e[i + 1]) / math.log(2) >= 1.5 for i in range(2))
+    e = [run(N, m.CurvatureTerm(lambda x, t: -0.1), lambda r: np.sqrt(r * r + 0.2 * 0.2) - 0.7, 0.7) for N in (30, 60, 120)]
+    assert all(math.log(e[i] / e[i + 1]) / math.log(2) >= 1.5 for i in range(2))
+
+
+def test_reference_eikonal_and_nan_robustness(m):
+    g = m.CartesianGrid((-1.0,), (1.0,), (101,))
+    phi = m.MeshField(lambda x: 2 * (x[0] - 0.3), g)
+    eq = m.LevelSetEquation(terms=(m.EikonalReinitializationTerm(phi),), ic=phi, bc=m.LinearExtrapolationBC())
+    m.integrate(eq, 2.0)
+    out, x = eq.state.peek(), g.coords()[0]
+    assert np.where(np.abs(out) > 0.5, 0.0, np.abs(out - (x - 0.3))).max() < 0.05
+    g2 = m.CartesianGrid((-2.0, -2.0), (2.0, 2.0), (31, 31))
+    phi2 = m.MeshField(lambda x: np.sqrt(x[0] ** 2 + x[1] ** 2) - 0.7, g2)
+    eq2 = m.LevelSetEquation(terms=(m.CurvatureTerm(lambda x, t: -0.1),), ic=phi2, bc=m.NeumannBC(), integrator=m.RK2())
+    m.integrate(eq2, 0.1)
+    assert not np.isnan(eq2.state.peek()).any()
+    g3 = m.CartesianGrid((-1.0,), (1.0,), (31,))
+    eq3 = m.LevelSetEquation(terms=(m.EikonalReinitializationTerm(),), ic=m.MeshField(lambda x: 0.0 * x[0], g3),
+                             bc=m.NeumannBC(), integrator=m.RK2())
+    m.integrate(eq3, 0.1)
+    assert not np.isnan(eq3.state.peek()).any()
+
+
+# ------------------------------------------------------------------------------------------------
+# API semantics: hooks, update_func, incremental integrate!, ic untouched
+# ------------------------------------------------------------------------------------------------
+def test_hooks_update_func_and_incremental(m, O):
+    case = H.c1_circle_rotation(48)
+    phi = case.engine_field(m)
+    terms = case.engine_terms(m, phi)
+    before = phi.peek().copy()
+    eq = m.LevelSetEquation(terms=terms, ic=phi, integrator=m.RK3())
+    calls = {"pre": 0, "post": 0, "upd": 0}
+    # two-leg integration with hooks == one-leg device loop (hooks here only count)
+    m.integrate(eq, 0.05, prehook=lambda e: calls.__setitem__("pre", calls["pre"] + 1),
+                posthook=lambda e: calls.__setitem__("post", calls["post"] + 1))
+    m.integrate(eq, 0.1)
+    assert calls["pre"] == calls["post"] > 0 and eq.t == 0.1
+    assert np.array_equal(phi.peek(), before)                     # ic never mutated (levelsetequation.jl:66)
+    fo = case.oracle_field()
+    O.integrate(fo, O.RK3, case.oracle_terms(), 0.05)
+    O.integrate(fo, O.RK3, case.oracle_terms(), 0.1, t0=0.05)
+    assert np.abs(fo.vals - eq.state.peek()).max() <= 1e-12
+    # update_func hook semantics (test-velocityextension.jl:4-17): called as f(coeff, phi, t) before the CFL and every stage
+    g = m.CartesianGrid((-1.0, -1.0), (1.0, 1.0), (21, 21))
+    p = m.MeshField(lambda x: np.sqrt(x[0] ** 2 + x[1] ** 2) - 0.5, g, bc=m.PeriodicBC())
+    v = m.MeshField(np.zeros((21, 21)), g)
+    seen = []
+
+    def upd(speed, phi_stage, t):
+        speed.vals[...] = 2 * t + 0.1
+        seen.append(t)
+
+    term = m.NormalMotionTerm(v, upd)
+    m.update_term(term, p, 0.3)
+    assert np.all(v.peek() == 0.7)
+    eq = m.LevelSetEquation(terms=(term,), ic=p, integrator=m.RK3())
+    m.integrate(eq, 1e-3, 5e-4)
+    assert eq.steps_taken == 2 and len(seen) == 1 + 2 * (1 + 3)     # CFL refresh + 3 stages per step
+    assert np.isfinite(eq.state.peek()).all()
+
+
+def test_counters_and_launch_accounting(m):
+    ctx = m.default_context()
+    case = H.c3_enright(32)
+    phi = case.engine_field(m)
+    eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=m.RK3())
+    eq.state.device()
+    ctx.reset_counters()
+    m.integrate(eq, 0.02)
+    c = ctx.counters()
+    assert c["stage_launches"] == 3 * eq.steps_taken
+    assert c["cfl_passes"] == eq.steps_taken          # cos(pi t/T) scale changes every step -> one CFL pass per step
+    assert c["kernel_launches"] == c["stage_launches"] + c["cfl_passes"]
