@@ -119,6 +119,12 @@ int32_t lsm_set_option(lsm_ctx* ctx, int32_t option, int32_t value);
 int32_t lsm_get_counters(lsm_ctx* ctx, lsm_counters* out);
 int32_t lsm_reset_counters(lsm_ctx* ctx);
 
+/* CUDA-event timing on the context's compute stream (the stream every kernel of this library is
+ * launched on): record into slot 0..7, then read the elapsed milliseconds between two slots
+ * (synchronises on the later event). */
+int32_t lsm_event_record(lsm_ctx* ctx, int32_t slot);
+int32_t lsm_event_elapsed_ms(lsm_ctx* ctx, int32_t slot_start, int32_t slot_stop, double* ms_out);
+
 /* Pin / unpin a host array (e.g. the memory of a Julia Array) so uploads/downloads run at full
  * PCIe speed.  Optional. */
 int32_t lsm_host_register(void* ptr, int64_t bytes);

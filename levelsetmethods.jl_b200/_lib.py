@@ -74,6 +74,8 @@ SYMBOLS = {
     "lsm_set_option": (_i32, [_vp, _i32, _i32]),
     "lsm_get_counters": (_i32, [_vp, C.POINTER(lsm_counters)]),
     "lsm_reset_counters": (_i32, [_vp]),
+    "lsm_event_record": (_i32, [_vp, _i32]),
+    "lsm_event_elapsed_ms": (_i32, [_vp, _i32, _i32, _pdbl]),
     "lsm_host_register": (_i32, [_vp, _i64]),
     "lsm_host_unregister": (_i32, [_vp]),
     "lsm_slab_plan": (_i32, [_i32, _i32, _i32, _pi32, _pi32]),

@@ -74,6 +74,14 @@ class Context:
     def reset_counters(self):
         L.check(L.lib().lsm_reset_counters(self.handle))
 
+    def event_record(self, slot: int):
+        L.check(L.lib().lsm_event_record(self.handle, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double()
+        L.check(L.lib().lsm_event_elapsed_ms(self.handle, a, b, C.byref(ms)))
+        return ms.value
+
     def slab(self, n_last: int):
         """(first, count) of the planes of the last dimension this rank owns (0-based first)."""
         f, c = C.c_int32(), C.c_int32()

@@ -64,6 +64,7 @@ struct lsm_ctx {
     std::vector<CflCacheEntry> cfl_cache;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;     // pending stage timings
     std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t ev_user[8] = {};
 };
 
 struct lsm_field {
@@ -542,6 +543,7 @@ int32_t lsm_ctx_destroy(lsm_ctx* c) {
     cudaDeviceSynchronize();
     resolve_timings(c);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    for (auto e : c->ev_user) if (e) cudaEventDestroy(e);
     if (c->nccl_comm) nccl().CommDestroy(c->nccl_comm);
     if (c->d_scalar) cudaFree(c->d_scalar);
     if (c->h_scalar) cudaFreeHost(c->h_scalar);
@@ -584,6 +586,24 @@ int32_t lsm_reset_counters(lsm_ctx* c) {
     if (!c) return fail(LSM_ERR_ARG, "null context");
     resolve_timings(c);
     c->cnt = lsm_counters{};
+    return LSM_OK;
+}
+
+int32_t lsm_event_record(lsm_ctx* c, int32_t slot) {
+    if (!c || slot < 0 || slot >= 8) return fail(LSM_ERR_ARG, "bad event slot");
+    CU(cudaSetDevice(c->device));
+    if (!c->ev_user[slot]) CU(cudaEventCreate(&c->ev_user[slot]));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));     // fold in outstanding halo traffic
+    CU(cudaEventRecord(c->ev_user[slot], c->stream));
+    return LSM_OK;
+}
+int32_t lsm_event_elapsed_ms(lsm_ctx* c, int32_t a, int32_t b, double* ms_out) {
+    if (!c || !ms_out || a < 0 || a >= 8 || b < 0 || b >= 8 || !c->ev_user[a] || !c->ev_user[b]) return fail(LSM_ERR_ARG, "bad event slot");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->ev_user[b]));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev_user[a], c->ev_user[b]));
+    *ms_out = ms;
     return LSM_OK;
 }
 

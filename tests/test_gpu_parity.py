@@ -320,6 +320,7 @@ def test_counters_and_launch_accounting(m):
     phi = case.engine_field(m)
     eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=m.RK3())
     eq.state.device()
+    eq.terms[0].velocity.base.device()            # upload the coefficient (one AoS->SoA kernel) before counting
     ctx.reset_counters()
     m.integrate(eq, 0.02)
     c = ctx.counters()
