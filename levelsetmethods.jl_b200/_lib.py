@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "liblsm_b200.so")
+SO_PATH = os.environ.get("LSM_B200_SO") or os.path.join(_HERE, "liblsm_b200.so")   # override: tuning builds only
 CSRC = os.path.join(_HERE, "csrc")
 
 # ---- enums (mirror include/lsm_b200.h) -----------------------------------------------------------

@@ -249,28 +249,20 @@ int32_t exchange_halo(lsm_field* f, cudaStream_t s) {
     char* p = static_cast<char*>(f->p);
     const int nl = f->n[last], R = c->rank, G = c->nranks;
     auto plane_ptr = [&](int k) { return p + (ptrdiff_t)k * (ptrdiff_t)f->plane * (ptrdiff_t)es; };
+    // Wrap-around neighbours honour the reference's periodic rule (boundaryconditions.jl:107-119): node n
+    // duplicates node 1, so ghost(n+k) = node(1+k) and ghost(1-k) = node(n-k): the last rank ships its planes
+    // nl-4..nl-2 (not its very last plane) upward to rank 0, rank 0 ships its planes 1..3 downward to the last rank.
+    const int up = (R + 1 < G) ? R + 1 : (periodic ? 0 : -1);
+    const int down = (R > 0) ? R - 1 : (periodic ? G - 1 : -1);
+    const int top_first = (R + 1 < G) ? nl - HALO : nl - 1 - HALO;      // planes sent upward
+    const int bottom_first = (R > 0) ? 0 : 1;                            // planes sent downward
     NC(nccl().GroupStart());
-    // to the upper neighbour: my top planes -> its low ghosts; from it: its bottom planes -> my high ghosts
-    if (R + 1 < G) {
-        NC(nccl().Send(plane_ptr(nl - HALO), bytes, ncclInt8, R + 1, c->nccl_comm, s));
-        NC(nccl().Recv(plane_ptr(nl), bytes, ncclInt8, R + 1, c->nccl_comm, s));
-        c->cnt.halo_bytes_sent += (int64_t)bytes;
-    } else if (periodic) {
-        // wrap honouring the reference's periodic rule (boundaryconditions.jl:107-119): node n duplicates
-        // node 1, so ghost(n+k) = node(1+k): rank 0's planes 1..3; and my planes nl-4..nl-2 are rank 0's low ghosts
-        NC(nccl().Send(plane_ptr(nl - 1 - HALO), bytes, ncclInt8, 0, c->nccl_comm, s));
-        NC(nccl().Recv(plane_ptr(nl), bytes, ncclInt8, 0, c->nccl_comm, s));
-        c->cnt.halo_bytes_sent += (int64_t)bytes;
-    }
-    if (R > 0) {
-        NC(nccl().Send(plane_ptr(0), bytes, ncclInt8, R - 1, c->nccl_comm, s));
-        NC(nccl().Recv(plane_ptr(-HALO), bytes, ncclInt8, R - 1, c->nccl_comm, s));
-        c->cnt.halo_bytes_sent += (int64_t)bytes;
-    } else if (periodic) {
-        NC(nccl().Send(plane_ptr(1), bytes, ncclInt8, G - 1, c->nccl_comm, s));
-        NC(nccl().Recv(plane_ptr(-HALO), bytes, ncclInt8, G - 1, c->nccl_comm, s));
-        c->cnt.halo_bytes_sent += (int64_t)bytes;
-    }
+    // Every rank issues UPWARD traffic first, then DOWNWARD: NCCL matches the sends and receives of a pair of
+    // ranks in issue order, and with 2 ranks and a periodic axis both directions join the same pair.
+    if (up >= 0)   { NC(nccl().Send(plane_ptr(top_first), bytes, ncclInt8, up, c->nccl_comm, s)); c->cnt.halo_bytes_sent += (int64_t)bytes; }
+    if (down >= 0) { NC(nccl().Recv(plane_ptr(-HALO), bytes, ncclInt8, down, c->nccl_comm, s)); }
+    if (down >= 0) { NC(nccl().Send(plane_ptr(bottom_first), bytes, ncclInt8, down, c->nccl_comm, s)); c->cnt.halo_bytes_sent += (int64_t)bytes; }
+    if (up >= 0)   { NC(nccl().Recv(plane_ptr(nl), bytes, ncclInt8, up, c->nccl_comm, s)); }
     NC(nccl().GroupEnd());
     f->halo_valid = true;
     return LSM_OK;

@@ -11,6 +11,7 @@
 //   derivatives.jl:28-175, levelsetops.jl:197-244 curvature, levelsetterms.jl:73-265 terms,
 //   timestepping.jl:128-202 stage combinations.
 #include "lsm_dev.cuh"
+#include "lsm_bc.cuh"
 #include "lsm_kernels.h"
 
 namespace lsm {
@@ -29,61 +30,6 @@ __device__ __forceinline__ double limiter(double x, double y) {
 // Julia max(): NaN-propagating
 __device__ __forceinline__ double jl_max(double a, double b) {
     return (isnan(a) || isnan(b)) ? __longlong_as_double(0x7FF8000000000000LL) : (b > a ? b : a);
-}
-
-// boundaryconditions.jl:90-97
-__device__ inline double lagrange_w(int j, int k, int P) {
-    double w = 1.0;
-    for (int m = 0; m <= P; ++m) {
-        if (m == j) continue;
-        w *= double(-k - m) / double(j - m);
-    }
-    return w;
-}
-
-// meshfield.jl:248-260 with bc_stencil inlined.  0-based indices.
-template <int N, class T, int DIM>
-__device__ T read_bc(const View<T>& v, int i0, int i1, int i2) {
-    if constexpr (DIM == 0) {
-        return v.p[(long)i0 + (long)i1 * v.s1 + (long)i2 * v.s2];
-    } else {
-        constexpr int d = DIM - 1;
-        const int i = d == 0 ? i0 : (d == 1 ? i1 : i2);
-        const int n = v.n[d];
-        if (i >= 0 && i < n) return read_bc<N, T, DIM - 1>(v, i0, i1, i2);
-        const BCDev bc = i < 0 ? v.bc[d][0] : v.bc[d][1];
-        if (bc.kind == BC_HALO) return read_bc<N, T, DIM - 1>(v, i0, i1, i2);   // stored ghost plane
-        auto rd = [&](int j) -> T {
-            return read_bc<N, T, DIM - 1>(v, d == 0 ? j : i0, d == 1 ? j : i1, d == 2 ? j : i2);
-        };
-        T acc = T(0);
-        if (bc.kind == BC_PERIODIC) {
-            // boundaryconditions.jl:107-119 (1-based: i<1 -> n-(1-i); i>n -> 1+(i-n)); the reference
-            // re-enters getindex when one wrap is not enough (tiny grids) — same as wrapping again.
-            int j = i;
-            for (int it = 0; it < 64 && (j < 0 || j >= n); ++it) j = j < 0 ? (n - 1) + j : 1 + j - n;
-            if (j < 0 || j >= n) return T(__longlong_as_double(0x7FF8000000000000LL));
-            acc += T(1.0) * rd(j);
-        } else if (bc.kind == BC_EXTRAP) {
-            const int k = i < 0 ? -i : i - (n - 1);
-            const int b = i < 0 ? 0 : n - 1;
-            const int dd = i < 0 ? 1 : -1;
-            for (int j = 0; j <= bc.P; ++j) acc += T(lagrange_w(j, k, bc.P)) * rd(b + dd * j);
-        } else if (bc.kind == BC_SYMMETRY) {
-            int j = i;
-            for (int it = 0; it < 64 && (j < 0 || j >= n); ++it) j = j < 0 ? -j : 2 * (n - 1) - j;
-            if (j < 0 || j >= n) return T(__longlong_as_double(0x7FF8000000000000LL));
-            acc += T(1.0) * rd(j);
-        } else {
-            return T(__longlong_as_double(0x7FF8000000000000LL));   // no BC: the reference throws
-        }
-        return acc;
-    }
-}
-
-template <int N, class T>
-__device__ __noinline__ T getindex_slow(const View<T>& v, int i0, int i1, int i2) {
-    return read_bc<N, T, N>(v, i0, i1, i2);
 }
 
 template <int N, class T>
@@ -377,26 +323,79 @@ template <int N, class T>
 __global__ void __launch_bounds__(256) cfl_kernel(const __grid_constant__ CflParams P) {
     const TermDev& t = P.term;
     const long total = (long)P.n[0] * P.n[1] * P.n[2];
+    const long stride = (long)gridDim.x * blockDim.x;
     unsigned long long best = 0ULL;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int i0 = (int)(idx % P.n[0]);
-        const long q = idx / P.n[0];
-        const int i1 = (int)(q % P.n[1]);
-        const int i2 = (int)(q / P.n[1]);
-        double s;
-        if (t.kind == TERM_ADVECTION) {
-            s = 0.0;
-#pragma unroll
-            for (int d = 0; d < N; ++d) {
-                const double v = coef_comp<T>(t, idx, d, i0, i1, i2, N);
-                const double q2 = fabs(v) / P.h[d];
-                s = (d == 0) ? q2 : s + q2;
-            }
-        } else {
-            s = fabs(coef_comp<T>(t, idx, 0, i0, i1, i2, N));
-        }
+    auto fold = [&](double s) {
         const unsigned long long bits = isnan(s) ? 0x7FF8000000000000ULL : (unsigned long long)__double_as_longlong(s);
         best = bits > best ? bits : best;
+    };
+    if (t.coef_kind == COEF_FIELD && !t.coef_f64) {
+        // stored coefficient: a pure streaming pass, no index decode; 4 independent loads in flight per thread
+        const T* __restrict__ c = static_cast<const T*>(t.coef);
+        const double g = t.scaled ? t.g : 1.0;
+        long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; idx + 3 * stride < total; idx += 4 * stride) {
+            double s[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long l = idx + k * stride;
+                if (t.kind == TERM_ADVECTION) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int d = 0; d < N; ++d) {
+                        double v = double(c[(long)d * t.cstride + l]);
+                        if (t.scaled) v = v * g;
+                        const double q = fabs(v) / P.h[d];
+                        acc = (d == 0) ? q : acc + q;
+                    }
+                    s[k] = acc;
+                } else {
+                    double v = double(c[l]);
+                    if (t.scaled) v = v * g;
+                    s[k] = fabs(v);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) fold(s[k]);
+        }
+        for (; idx < total; idx += stride) {
+            double acc;
+            if (t.kind == TERM_ADVECTION) {
+                acc = 0.0;
+#pragma unroll
+                for (int d = 0; d < N; ++d) {
+                    double v = double(c[(long)d * t.cstride + idx]);
+                    if (t.scaled) v = v * g;
+                    const double q = fabs(v) / P.h[d];
+                    acc = (d == 0) ? q : acc + q;
+                }
+            } else {
+                double v = double(c[idx]);
+                if (t.scaled) v = v * g;
+                acc = fabs(v);
+            }
+            fold(acc);
+        }
+    } else {
+        for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+            const int i0 = (int)(idx % P.n[0]);
+            const long q = idx / P.n[0];
+            const int i1 = (int)(q % P.n[1]);
+            const int i2 = (int)(q / P.n[1]);
+            double s;
+            if (t.kind == TERM_ADVECTION) {
+                s = 0.0;
+#pragma unroll
+                for (int d = 0; d < N; ++d) {
+                    const double v = coef_comp<T>(t, idx, d, i0, i1, i2, N);
+                    const double q2 = fabs(v) / P.h[d];
+                    s = (d == 0) ? q2 : s + q2;
+                }
+            } else {
+                s = fabs(coef_comp<T>(t, idx, 0, i0, i1, i2, N));
+            }
+            fold(s);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
