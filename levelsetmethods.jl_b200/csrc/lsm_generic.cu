@@ -335,28 +335,33 @@ __global__ void __launch_bounds__(256) cfl_kernel(const __grid_constant__ CflPar
         const double g = t.scaled ? t.g : 1.0;
         long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
         for (; idx + 3 * stride < total; idx += 4 * stride) {
-            double s[4];
+            // issue all loads before the first division: the IEEE-division slow-path branch would otherwise
+            // fence every load behind the previous quotient and expose DRAM latency 4*N times per iteration
+            double v[4][N];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int d = 0; d < N; ++d)
+                    v[k][d] = t.kind == TERM_ADVECTION ? double(c[(long)d * t.cstride + idx + k * stride])
+                                                       : (d == 0 ? double(c[idx + k * stride]) : 0.0);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const long l = idx + k * stride;
                 if (t.kind == TERM_ADVECTION) {
                     double acc = 0.0;
 #pragma unroll
                     for (int d = 0; d < N; ++d) {
-                        double v = double(c[(long)d * t.cstride + l]);
-                        if (t.scaled) v = v * g;
-                        const double q = fabs(v) / P.h[d];
+                        double w = v[k][d];
+                        if (t.scaled) w = w * g;
+                        const double q = fabs(w) / P.h[d];
                         acc = (d == 0) ? q : acc + q;
                     }
-                    s[k] = acc;
+                    fold(acc);
                 } else {
-                    double v = double(c[l]);
-                    if (t.scaled) v = v * g;
-                    s[k] = fabs(v);
+                    double w = v[k][0];
+                    if (t.scaled) w = w * g;
+                    fold(fabs(w));
                 }
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) fold(s[k]);
         }
         for (; idx < total; idx += stride) {
             double acc;
