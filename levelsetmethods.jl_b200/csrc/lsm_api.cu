@@ -184,6 +184,7 @@ View<T> make_view(const lsm_field* f) {
     for (int d = 0; d < 3; ++d) v.n[d] = f->n[d];
     v.s1 = f->ndim > 1 ? (long)f->n[0] : 0;
     v.s2 = f->ndim > 2 ? (long)f->n[0] * f->n[1] : 0;
+    v.halo = f->halo; v._pad = 0;
     const lsm_ctx* c = f->ctx;
     const int last = f->ndim - 1;
     for (int d = 0; d < 3; ++d)

@@ -33,6 +33,8 @@ struct View {
     int n[3];            // owned nodes per dim (1 for unused dims)
     long s1, s2;         // element strides of dim 2 and dim 3 (dim 1 is contiguous)
     BCDev bc[3][2];      // BC_HALO on a side whose ghost planes are stored
+    int halo;            // ghost planes of the last dimension stored before the first owned node (0 or 3)
+    int _pad;
 };
 
 struct TermDev {

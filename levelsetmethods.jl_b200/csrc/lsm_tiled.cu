@@ -20,13 +20,16 @@
 //         u * (u > 0 ? weno5- : weno5+) into (|u|/h) * W(q) with no selects; W works on undivided
 //         differences (WENO5 is homogeneous of degree 1), smoothness indicators and candidates are
 //         written on second differences, the three weight divisions + three normalisations become
-//         ONE reciprocal (MUFU.RCP64H + 2 Newton steps), and max(v^2) runs on the integer pipe:
+//         ONE reciprocal (MUFU.RCP64H + 2 Newton steps), and max(v^2) is a compare-select chain:
 //         ~47 DP instructions per evaluation instead of ~65 + 6 divisions (13.6 slots each);
 //       - Godunov/ENO2 terms use undivided differences and the positive homogeneity of minmod;
 //       - curvature uses kappa*|grad phi| = (tr(H) q - g'Hg)/q, i.e. no pow() and no sqrt().
 //
 // Compiled with FMA contraction ON.  Parity with the CPU oracle is checked in tests/ (<= 1e-10 after
 // 100 RK3 steps in Float64, <= 1e-4 in Float32).
+#include <cstdint>
+#include <cstdlib>
+#include <cuda.h>          // CUtensorMap + enums only; cuTensorMapEncodeTiled is looked up at run time (no libcuda link)
 #include "lsm_dev.cuh"
 #include "lsm_bc.cuh"
 #include "lsm_kernels.h"
@@ -46,30 +49,67 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc, int b
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// 1/x for a positive normal x: MUFU.RCP64H seed + two Newton steps (relative error ~1e-16)
+// ---- TMA (cp.async.bulk.tensor) + mbarrier: one elected thread copies a whole (tile + halo) plane -----------
+struct TmaMaps {
+    int enabled;                       // tensor maps below are valid
+    int _pad[15];
+    alignas(64) CUtensorMap phi;       // stage input incl. its ghost planes: dims (n0, n1, halo + n2 + halo)
+    alignas(64) CUtensorMap aux[8];    // staged coefficient components and phi^n: dims (n0, n1, n2)
+};
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LSM_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LSM_DONE_%=;\n"
+        "bra LSM_WAIT_%=;\n"
+        "LSM_DONE_%=:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// 1/x for a positive normal x: MUFU.RCP64H seed (uses the top 32 bits of x: relative error ~2^-20) + Newton steps.
+// STEPS = 2 gives ~1e-16; STEPS = 1 gives ~1e-12, enough where the quotient is a small correction term
+// (WENO5: W = d2 + num/den with |num/den| <= max|e_k| << |d|).
+template <int STEPS>
 __device__ __forceinline__ double fast_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double t = fma(-x, y, 1.0);
-    y = fma(y, t, y);
-    t = fma(-x, y, 1.0);
-    y = fma(y, t, y);
+#pragma unroll
+    for (int k = 0; k < STEPS; ++k) {
+        const double t = fma(-x, y, 1.0);
+        y = fma(y, t, y);
+    }
     return y;
 }
 
-// max(|a|..|e|) exactly, on the integer pipe (non-negative doubles order like unsigned integers)
+// The element of largest magnitude among a..e (exact; only its square is used).  A plain compare-select is
+// DSETP + 2 SEL (~1 DP slot, measured 60 lane-ops/clk/SM for compare-select + add in tools/fp64_peak.cu), whereas
+// fmax() carries NaN-handling code (~3.7 slots).  NaN inputs poison the smoothness indicators anyway.
 __device__ __forceinline__ double absmax5(double a, double b, double c, double d, double e) {
-    auto key = [](double x) -> unsigned long long {
-        return ((unsigned long long)((unsigned)__double2hiint(x) & 0x7fffffffu) << 32) | (unsigned)__double2loint(x);
-    };
-    unsigned long long m = key(a), k;
-    k = key(b); m = k > m ? k : m;
-    k = key(c); m = k > m ? k : m;
-    k = key(d); m = k > m ? k : m;
-    k = key(e); m = k > m ? k : m;
-    return __longlong_as_double((long long)m);
+    double m = a;
+    m = fabs(b) > fabs(m) ? b : m;
+    m = fabs(c) > fabs(m) ? c : m;
+    m = fabs(d) > fabs(m) ? d : m;
+    m = fabs(e) > fabs(m) ? e : m;
+    return m;
 }
+__device__ __forceinline__ double pos_part(double x) { return x > 0.0 ? x : 0.0; }   // levelsetterms.jl:180
+__device__ __forceinline__ double neg_part(double x) { return x < 0.0 ? x : 0.0; }   // levelsetterms.jl:181
 
 // Undivided upwind WENO5: given six samples in upwind order (q3 is the node, q0 the far upwind
 // end), returns h * weno5 of the reference (derivatives.jl:61-121), i.e. the reference value is
@@ -102,7 +142,35 @@ __device__ __forceinline__ double weno5_up(T q0, T q1, T q2, T q3, T q4, T q5) {
     const double G2 = fma(2.0, e3, e2);
     const double G3 = fma(2.0, e3, -0.5 * e4);
     const double num = fma(w3, G3, fma(w2, G2, w1 * G1));
-    return fma(num, fast_rcp(den), d2);
+    return fma(num, fast_rcp<1>(den), d2);
+}
+
+// Float32 fields: the same evaluation entirely in FP32 (FFMA issues at <= 1 slot, FP64 at 2; BASELINE tolerance for
+// Float32 is 1e-4 against the oracle, which follows Julia's promotion to Float64 after the first difference).
+// Range safety in FP32: the differences are normalised by 1/max|d| before squaring, so b_k = 4(S_k + eps)/max(d^2)
+// lies in [4e-6, ~1e2], the weights in [1e-22, 1e8], and eps = 1e-6*max(v^2) becomes the exact constant 4e-6
+// (flat data: max|d| = 0 -> all b_k equal -> result d2 = 0, finite).
+template <>
+__device__ __forceinline__ double weno5_up<float>(float q0, float q1, float q2, float q3, float q4, float q5) {
+    const float d0 = q1 - q0, d1 = q2 - q1, d2 = q3 - q2, d3 = q4 - q3, d4 = q5 - q4;
+    const float e1 = d1 - d0, e2 = d2 - d1, e3 = d3 - d2, e4 = d4 - d3;
+    const float m = fmaxf(fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fmaxf(fabsf(d2), fabsf(d3))), fabsf(d4));
+    const float im = m > 0.f ? __frcp_rn(m) : 0.f;
+    const float s1 = e1 * im, s2 = e2 * im, s3 = e3 * im, s4 = e4 * im;
+    const float c133 = 13.0f / 3.0f;
+    const float t1a = s2 - s1, t1b = s3 - s2, t1c = s4 - s3;
+    const float t2a = fmaf(3.0f, s2, -s1), t2b = s2 + s3, t2c = fmaf(-3.0f, s3, s4);
+    const float b1 = fmaf(t2a, t2a, fmaf(c133, t1a * t1a, 4.0e-6f));
+    const float b2 = fmaf(t2b, t2b, fmaf(c133, t1b * t1b, 4.0e-6f));
+    const float b3 = fmaf(t2c, t2c, fmaf(c133, t1c * t1c, 4.0e-6f));
+    const float p12 = b1 * b2, p13 = b1 * b3, p23 = b2 * b3;
+    const float w1 = p23 * p23, w2 = p13 * p13, w3 = p12 * p12;
+    const float den = fmaf(3.0f, w3, fmaf(6.0f, w2, w1));
+    const float G1 = fmaf(5.0f / 6.0f, e2, (-1.0f / 3.0f) * e1);
+    const float G2 = fmaf(2.0f, e3, e2);
+    const float G3 = fmaf(2.0f, e3, -0.5f * e4);
+    const float num = fmaf(w3, G3, fmaf(w2, G2, w1 * G1));
+    return double(fmaf(num, __frcp_rn(den), d2));
 }
 
 // levelsetterms.jl:184-187
@@ -113,15 +181,20 @@ __device__ __forceinline__ double minmod(double x, double y) {
 
 template <class T, int NDIM, int TX, int TY, int NY>
 struct TileGeom {
-    static constexpr int W = TX + 2 * HAL;
+    // A TMA box must start at a 16-byte-aligned element (measured: tools/tma_probe.cu — a Float64 box at an odd x
+    // faults with "illegal instruction"), so the tile starts XL = 4 columns left of x0 (one unused column on each
+    // side of the 3-cell halo) and rows are W = TX + 8 wide for both dtypes.
+    static constexpr int XL = 4;
+    static constexpr int W = TX + 2 * XL;
     static constexpr int HH = TY * NY + 2 * HAL;
-    static constexpr int PLANE = W * HH;          // phi plane: tile + halo
+    static constexpr int PLANE = ((W * HH + 31) / 32) * 32;              // slot stride: tile + halo, padded to 128 B
     static constexpr int TILE = TX * TY * NY;     // owned nodes of one plane of the tile
     static constexpr int NT = TX * TY;
     static constexpr int NW = NT / 32;
-    static constexpr int RING = NDIM == 3 ? 2 * HAL + 2 : 1;
-    static constexpr int NBUF = NDIM == 3 ? 2 : 1;        // aux double buffering along z
-    static size_t smem_bytes(int naux) { return ((size_t)RING * PLANE + (size_t)NBUF * naux * TILE) * sizeof(T); }
+    static constexpr int PD = 1;                                    // planes prefetched ahead of the one being computed (2 measured no faster, costs smem)
+    static constexpr int RING = NDIM == 3 ? 2 * HAL + 1 + PD : 1;   // phi planes resident in shared memory
+    static constexpr int NBUF = NDIM == 3 ? PD + 1 : 1;             // aux tiles (coefficients, phi^n) in flight
+    static size_t smem_bytes(int naux) { return ((size_t)RING * PLANE + (size_t)NBUF * naux * TILE) * sizeof(T) + 128 + 16; }   // + alignment slack + mbarrier
 };
 
 // stored coefficient components and phi^n staged in shared memory next to the phi ring
@@ -157,12 +230,14 @@ __device__ __forceinline__ int remap_index(int i, int n, int kind_lo, int kind_h
 // (x = base; x -= c*H_1; x -= c*H_2; ..., timestepping.jl:128-202).
 template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, int TX, int TY, int NY, int MINB>
 __global__ void __launch_bounds__(TX * TY, MINB)
-stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ AuxList A, const int cz) {
+stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ AuxList A, const __grid_constant__ TmaMaps M, const int cz) {
     using G = TileGeom<T, NDIM, TX, TY, NY>;
     constexpr int RING = G::RING;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* const ring = reinterpret_cast<T*>(smem_raw);
+    unsigned char* const sm128 = smem_raw + ((128u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u);   // TMA wants 128 B
+    T* const ring = reinterpret_cast<T*>(sm128);
     T* const aux = ring + (size_t)RING * G::PLANE;                   // [NBUF][naux][TILE]
+    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(aux + (size_t)G::NBUF * A.n * G::TILE);
 
     const int n0 = P.in.n[0], n1 = P.in.n[1], n2 = NDIM == 3 ? P.in.n[2] : 1;
     const long vs1 = P.in.s1, vs2 = NDIM == 3 ? P.in.s2 : 0;
@@ -180,95 +255,156 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
     // whole tile + halo inside the stored x-y extent -> plain copies; otherwise resolve ghosts
     const bool y_lo_ok = (y0 - HAL >= 0) || (NDIM == 2 && P.in.bc[1][0].kind == BC_HALO);
     const bool y_hi_ok = (y0 + TY * NY + HAL <= n1) || (NDIM == 2 && P.in.bc[1][1].kind == BC_HALO);
-    const bool xy_in = (x0 - HAL >= 0) && (x0 + TX + HAL <= n0) && y_lo_ok && y_hi_ok;
+    const bool xy_in = (x0 - G::XL >= 0) && (x0 - G::XL + G::W <= n0) && y_lo_ok && y_hi_ok;
     const int kzl = P.in.bc[2][0].kind, kzh = P.in.bc[2][1].kind;
+    // TMA fill (one cp.async.bulk.tensor per plane, issued by thread 0, completed on an mbarrier) for tiles that need
+    // no ghost resolution; everything else goes through the LDGSTS paths below.
+    const bool tma_phi = NDIM == 3 && (M.enabled == 1 || M.enabled == 2) && xy_in;
+    const bool tma_aux = NDIM == 3 && (M.enabled == 1 || M.enabled == 3) && (x0 + TX <= n0) && (y0 + TY * NY <= n1);
+    const bool leader = (tx | ty) == 0;
+    unsigned phase = 0;
+    if (NDIM == 3 && M.enabled) {
+        if (leader) mbar_init(bar, 1);
+        __syncthreads();
+    }
 
-    // one warp per row of the (tile + halo) plane: lanes 0..31 copy columns 0..31, lanes 0..W-33 also 32..W-1
-    auto load_phi = [&](int z) {
-        T* dst = ring + ((z + 1024) & (RING - 1)) * G::PLANE;
-        const bool z_plain = NDIM == 2 || ((z >= 0 || kzl == BC_HALO) && (z < n2 || kzh == BC_HALO));
-        if (xy_in && z_plain) {
-            const T* src = vp + (long)(x0 - HAL) + (long)(y0 - HAL) * vs1 + (long)z * vs2;
-            for (int r = warp; r < G::HH; r += G::NW) {
-                const T* s = src + (long)r * vs1;
-                T* d = dst + r * G::W;
-                cp_async(d + lane, s + lane, sizeof(T) == 8);
-                if (lane < G::W - 32) cp_async(d + 32 + lane, s + 32 + lane, sizeof(T) == 8);
-            }
-        } else if (REMAP) {
-            const int zz = NDIM == 3 ? remap_index(z, n2, kzl, kzh) : 0;
+    // ---- ring fill.  One warp per row of the (tile + halo) plane: lanes 0..31 copy columns 0..31, lanes 0..W-33
+    // also columns 32..W-1.  The source address of a thread's element is  rowptr + zz * vs2, where rowptr depends
+    // only on the thread (x / y ghost remap included) and zz only on the plane, so everything per-thread is hoisted
+    // out of the z loop and a copy costs one 64-bit add.
+    constexpr int RPW = (G::HH + G::NW - 1) / G::NW;          // rows per warp
+    const T* rowp[RPW];
+    int dxb;                                                  // column offset of the second element (32 unless clamped)
+    {
+        int gxa = x0 - G::XL + lane, gxb = x0 - G::XL + 32 + lane;
+        if (!xy_in && REMAP) {
             // columns / rows beyond the grid + halo of a partial tile are never read: clamp them into range
-            const int gxa = min(max(remap_index(x0 - HAL + lane, n0, P.in.bc[0][0].kind, P.in.bc[0][1].kind), 0), n0 - 1);
-            const int gxb = min(max(remap_index(x0 - HAL + 32 + lane, n0, P.in.bc[0][0].kind, P.in.bc[0][1].kind), 0), n0 - 1);
-            for (int r = warp; r < G::HH; r += G::NW) {
-                int gy = remap_index(y0 - HAL + r, n1, P.in.bc[1][0].kind, P.in.bc[1][1].kind);
+            gxa = min(max(remap_index(gxa, n0, P.in.bc[0][0].kind, P.in.bc[0][1].kind), 0), n0 - 1);
+            gxb = min(max(remap_index(gxb, n0, P.in.bc[0][0].kind, P.in.bc[0][1].kind), 0), n0 - 1);
+        }
+        dxb = gxb - gxa;
+#pragma unroll
+        for (int m = 0; m < RPW; ++m) {
+            int gy = y0 - HAL + warp + m * G::NW;
+            if (!xy_in && REMAP) {
+                gy = remap_index(gy, n1, P.in.bc[1][0].kind, P.in.bc[1][1].kind);
                 if (NDIM == 2) gy = min(max(gy, P.in.bc[1][0].kind == BC_HALO ? -HAL : 0), P.in.bc[1][1].kind == BC_HALO ? n1 - 1 + HAL : n1 - 1);
                 else gy = min(max(gy, 0), n1 - 1);
-                const T* s = vp + (long)gy * vs1 + (long)zz * vs2;
-                T* d = dst + r * G::W;
-                cp_async(d + lane, s + gxa, sizeof(T) == 8);
-                if (lane < G::W - 32) cp_async(d + 32 + lane, s + gxb, sizeof(T) == 8);
+            }
+            rowp[m] = vp + (long)gy * vs1 + gxa;
+        }
+    }
+    const int dst0 = warp * G::W + lane;                      // element offset of row `warp`, column `lane` in a slot
+    auto load_phi = [&](int z, int slot, unsigned& txb) {
+        T* dst = ring + slot * G::PLANE + dst0;
+        const bool z_plain = NDIM == 2 || ((z >= 0 || kzl == BC_HALO) && (z < n2 || kzh == BC_HALO));
+        if (tma_phi && z_plain) {
+            if (leader) tma_load_3d(ring + slot * G::PLANE, &M.phi, x0 - G::XL, y0 - HAL, z + P.in.halo, bar);
+            txb += (unsigned)(G::W * G::HH * sizeof(T));
+        } else if (REMAP || (xy_in && z_plain)) {
+            const int zz = (NDIM == 3 && REMAP) ? remap_index(z, n2, kzl, kzh) : z;
+            const long zoff = NDIM == 3 ? (long)zz * vs2 : 0;
+#pragma unroll
+            for (int m = 0; m < RPW; ++m) {
+                if (RPW * G::NW == G::HH || warp + m * G::NW < G::HH) {
+                    const T* sp = rowp[m] + zoff;
+                    cp_async(dst + m * G::NW * G::W, sp, sizeof(T) == 8);
+                    if (lane < G::W - 32) cp_async(dst + m * G::NW * G::W + 32, sp + dxb, sizeof(T) == 8);
+                }
             }
         } else {
             for (int r = warp; r < G::HH; r += G::NW) {
-                T* d = dst + r * G::W;
-                d[lane] = getindex_slow<NDIM, T>(P.in, x0 - HAL + lane, y0 - HAL + r, z);
-                if (lane < G::W - 32) d[32 + lane] = getindex_slow<NDIM, T>(P.in, x0 - HAL + 32 + lane, y0 - HAL + r, z);
+                T* d = ring + slot * G::PLANE + r * G::W;
+                d[lane] = getindex_slow<NDIM, T>(P.in, x0 - G::XL + lane, y0 - HAL + r, z);
+                if (lane < G::W - 32) d[32 + lane] = getindex_slow<NDIM, T>(P.in, x0 - G::XL + 32 + lane, y0 - HAL + r, z);
             }
         }
     };
-    // stored coefficients and phi^n of the owned nodes of plane z
-    auto load_aux = [&](int z) {
-        T* dst = aux + (size_t)(z & (G::NBUF - 1)) * A.n * G::TILE;
+    // stored coefficients and phi^n of the owned nodes of plane z: per-thread node offsets are loop invariants
+    long aoff[NY];
 #pragma unroll
-        for (int k = 0; k < NY; ++k) {
-            const int r = ty + k * TY;
-            const int ii = x0 + tx, jj = y0 + r;
-            if (ii < n0 && jj < n1) {
-                const long node = (long)ii + (long)jj * vs1 + (long)z * vs2;
+    for (int k = 0; k < NY; ++k) {
+        const int ii = x0 + tx, jj = y0 + ty + k * TY;
+        aoff[k] = (ii < n0 && jj < n1) ? (long)ii + (long)jj * vs1 : -1;
+    }
+    auto load_aux = [&](int z, int buf, unsigned& txb) {
+        T* dst = aux + (size_t)buf * A.n * G::TILE + ty * TX + tx;
+        const long zoff = (long)z * vs2;
+        if (tma_aux) {
+            if (leader)
+                for (int a = 0; a < A.n; ++a) tma_load_3d(aux + ((size_t)buf * A.n + a) * G::TILE, &M.aux[a], x0, y0, z, bar);
+            txb += (unsigned)(A.n * G::TILE * sizeof(T));
+        } else for (int a = 0; a < A.n; ++a) {
+            const T* sp = static_cast<const T*>(A.src[a]) + zoff;
 #pragma unroll
-                for (int a = 0; a < 8; ++a)
-                    if (a < A.n) cp_async(dst + a * G::TILE + r * TX + tx, static_cast<const T*>(A.src[a]) + node, sizeof(T) == 8);
-            }
+            for (int k = 0; k < NY; ++k)
+                if (aoff[k] >= 0) cp_async(dst + a * G::TILE + k * TY * TX, sp + aoff[k], sizeof(T) == 8);
         }
     };
 
-    if (NDIM == 3) for (int z = zbeg - HAL; z <= zbeg + HAL; ++z) load_phi(z);
-    else load_phi(0);
-    load_aux(zbeg);
-    cp_async_commit();
-    cp_async_wait_all();
+    // Software pipeline (3-D): plane p lives in ring slot (p - (zbeg - HAL)) mod RING.  Iteration z issues the copies
+    // of plane z + HAL + PD and of the aux tiles of plane z + PD as ONE cp.async group, computes plane z, then waits
+    // until at most PD - 1 groups are pending — so a plane has PD iterations to arrive and DRAM latency is paid once
+    // per chunk, not once per plane.  The slot written in iteration z held plane z - HAL - 1, last read in z - 1.
+    constexpr int PD = G::PD;
+    static_assert(PD == 1, "the TMA mbarrier protocol below assumes one plane of prefetch");
+    {
+        unsigned txb = 0;
+        if (NDIM == 3) for (int p = 0; p <= 2 * HAL; ++p) load_phi(zbeg - HAL + p, p, txb);
+        else load_phi(0, 0, txb);
+        load_aux(zbeg, 0, txb);
+        if (txb && leader) mbar_expect_tx(bar, txb);
+        cp_async_commit();
+        cp_async_wait_all();
+        if (txb) { mbar_wait(bar, phase); phase ^= 1u; }
+    }
     __syncthreads();
 
     const double ih[3] = {1.0 / P.h[0], 1.0 / P.h[1], NDIM == 3 ? 1.0 / P.h[2] : 0.0};
     const int i = x0 + tx;
+    int s0 = 0;        // ring slot of plane z - HAL
+    int ab = 0;        // aux buffer of plane z
 
     for (int z = zbeg; z < zend; ++z) {
+        unsigned txb = 0;
         if (NDIM == 3) {
-            if (z + HAL + 1 <= zend - 1 + HAL) load_phi(z + HAL + 1);
-            if (z + 1 < zend) load_aux(z + 1);
+            int sl = s0 + 2 * HAL + PD; sl = sl >= RING ? sl - RING : sl;
+            int bf = ab + PD;           bf = bf >= G::NBUF ? bf - G::NBUF : bf;
+            if (z + HAL + PD <= zend - 1 + HAL) load_phi(z + HAL + PD, sl, txb);
+            if (z + PD < zend) load_aux(z + PD, bf, txb);
+            if (txb && leader) mbar_expect_tx(bar, txb);
             cp_async_commit();
         }
-        const T* cur = ring + ((z + 1024) & (RING - 1)) * G::PLANE;
-        const T* auxz = aux + (size_t)(z & (G::NBUF - 1)) * A.n * G::TILE;
+        // element offsets of the ring slots of planes z-3 .. z+3 (block-uniform)
+        int zo[2 * HAL + 1];
+#pragma unroll
+        for (int k = 0; k <= 2 * HAL; ++k) { int sl = s0 + k; sl = sl >= RING ? sl - RING : sl; zo[k] = NDIM == 3 ? sl * G::PLANE : 0; }
+        const T* cur = ring + zo[HAL];
+        const T* auxz = aux + (size_t)ab * A.n * G::TILE;
 #pragma unroll
         for (int k = 0; k < NY; ++k) {
             const int r = ty + k * TY;
             const int j = y0 + r;
             if (i < n0 && j < n1 && (NDIM == 3 || (j >= ylo && j < yhi))) {
-                const int sc = (r + HAL) * G::W + tx + HAL;
+                const int sc = (r + HAL) * G::W + tx + G::XL;
                 const int st = r * TX + tx;
                 const T* c0 = cur + sc;
                 const T qc = c0[0];
                 // sample at offset m along dimension d (all inside the tile + halo)
-                auto at = [&](int d, int m) -> T {
+                auto at = [&](int d, int m) -> T {          // m is a compile-time constant at every call site
                     if (d == 0) return c0[m];
                     if (d == 1) return c0[m * G::W];
-                    return ring[((z + m + 1024) & (RING - 1)) * G::PLANE + sc];
+                    return ring[zo[HAL + m] + sc];
+                };
+                // upwind-ordered sample: offset mult * s along d, s = +-1 (mult compile-time)
+                auto up = [&](int d, int mult, int s) -> T {
+                    if (d == 0) return c0[mult * s];
+                    if (d == 1) return c0[mult * s * G::W];
+                    return ring[(s > 0 ? zo[HAL + mult] : zo[HAL - mult]) + sc];
                 };
                 auto at2 = [&](int d1, int m1, int d2, int m2) -> T {      // d1 < d2
                     const int off = (d1 == 0 ? m1 : m1 * G::W) + (d2 == 1 ? m2 * G::W : 0);
-                    if (d2 == 2) return ring[((z + m2 + 1024) & (RING - 1)) * G::PLANE + sc + off];
+                    if (d2 == 2) return ring[zo[HAL + m2] + sc + off];
                     return c0[off];
                 };
                 // coefficient component d of term k (times g(t))
@@ -316,7 +452,7 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                         for (int d = 0; d < NDIM; ++d) {
                             const double u = coef(tm, kk, d);
                             const int s = u > 0 ? 1 : -1;       // upwind-ordered sampling: q_k = phi[i - s*(3-k)]
-                            const double w = weno5_up<T>(at(d, -3 * s), at(d, -2 * s), at(d, -s), qc, at(d, s), at(d, 2 * s));
+                            const double w = weno5_up<T>(up(d, -3, s), up(d, -2, s), up(d, -1, s), qc, up(d, 1, s), up(d, 2, s));
                             const double a = fabs(u) * ih[d];
                             H = d == 0 ? a * w : fma(a, w, H);
                         }
@@ -336,13 +472,15 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                             double ng, ps;
                             eno2(d, ng, ps);
                             const double i2 = ih[d] * ih[d];
-                            const double a = fmax(ng, 0.0), b = fmin(ps, 0.0), c = fmin(ng, 0.0), e = fmax(ps, 0.0);
+                            const double a = pos_part(ng), b = neg_part(ps), c = neg_part(ng), e = pos_part(ps);
                             gp = fma(fma(a, a, b * b), i2, gp);
                             gm = fma(fma(c, c, e * e), i2, gm);
                         }
                         if (tm.kind == TERM_NORMAL) {
                             const double v = coef(tm, kk, 0);
-                            H = fmax(v, 0.0) * sqrt(gp) + fmin(v, 0.0) * sqrt(gm);
+                            // positive(v)*sqrt(grad+) + negative(v)*sqrt(grad-): one of the two products is exactly 0
+                            // (a NaN speed gives 0 like positive()/negative() do)
+                            H = (v > 0 ? v : (v < 0 ? v : 0.0)) * sqrt(v > 0 ? gp : gm);
                         } else if (tm.coef_kind == COEF_NONE) {          // live sign, O&F 7.6 (levelsetterms.jl:237-242)
                             const double nrm = sqrt(qc > T(0) ? gp : gm);
                             const double den = sqrt(double(T(qc * qc)) + (nrm * nrm) * (P.dxmin * P.dxmin));
@@ -378,7 +516,7 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                         }
                         const double eps = sizeof(T) == 8 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
                         const double b = coef(tm, kk, 0);
-                        H = q < eps ? b * 0.0 : b * (fma(tr, q, -quad) * fast_rcp(q));
+                        H = q < eps ? b * 0.0 : b * (fma(tr, q, -quad) * fast_rcp<2>(q));
                     }
                     x = T(fma(-P.c, H, double(x)));
                     if (P.out2) x2 = T(fma(-P.c2, H, double(x2)));
@@ -395,8 +533,11 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
             }
         }
         if (NDIM == 3) {
-            cp_async_wait_all();
+            cp_async_wait_pending<PD - 1>();
+            if (txb) { mbar_wait(bar, phase); phase ^= 1u; }
             __syncthreads();
+            s0 = s0 + 1 == RING ? 0 : s0 + 1;
+            ab = ab + 1 == G::NBUF ? 0 : ab + 1;
         }
     }
 }
@@ -407,6 +548,36 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
 #define LSM_NY 2
 #define LSM_MINB 2
 #endif
+
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (liblsm_b200 does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <class T>
+bool encode_map3(CUtensorMap* m, const void* base, long n0, long n1, long nplanes, int b0, int b1) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)n0, (cuuint64_t)n1, (cuuint64_t)nplanes};
+    const cuuint64_t strides[2] = {(cuuint64_t)n0 * sizeof(T), (cuuint64_t)n0 * n1 * sizeof(T)};
+    const cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1u};
+    const cuuint32_t es[3] = {1u, 1u, 1u};
+    return enc(m, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims,
+               strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP>
 cudaError_t launch_tiled(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
@@ -421,6 +592,17 @@ cudaError_t launch_tiled(const StageParams<T>& P, const AuxList& A, cudaStream_t
         attr_smem = smem;
     }
     const View<T>& v = P.in;
+    // TMA tensor maps: 3-D, rows a multiple of 16 bytes, 16-byte aligned bases, and a grid big enough to care
+    TmaMaps M;
+    M.enabled = 0;
+    if (NDIM == 3 && (v.n[0] * sizeof(T)) % 16 == 0 && (long)v.n[0] * v.n[1] * v.n[2] >= 32L * 32 * 32 && !getenv("LSM_B200_NO_TMA")) {
+        const T* base = v.p - (long)v.halo * v.s2;
+        bool ok = ((uintptr_t)base % 16 == 0) && encode_map3<T>(&M.phi, base, v.n[0], v.n[1], (long)v.n[2] + 2L * v.halo, G::W, G::HH);
+        for (int a = 0; ok && a < A.n; ++a)
+            ok = ((uintptr_t)A.src[a] % 16 == 0) && encode_map3<T>(&M.aux[a], A.src[a], v.n[0], v.n[1], v.n[2], TX, TY * NY);
+        M.enabled = ok ? 1 : 0;
+        if (const char* md = getenv("LSM_B200_TMA_MODE")) M.enabled = ok ? atoi(md) : 0;   // debug: 1 both, 2 phi only, 3 aux only
+    }
     dim3 block(TX, TY), grid;
     int cz = 1;
     if (NDIM == 3) {
@@ -430,7 +612,7 @@ cudaError_t launch_tiled(const StageParams<T>& P, const AuxList& A, cudaStream_t
     } else {
         grid = dim3((v.n[0] + TX - 1) / TX, (v.n[1] + TY * NY - 1) / (TY * NY), 1);
     }
-    kern<<<grid, block, smem, s>>>(P, A, cz);
+    kern<<<grid, block, smem, s>>>(P, A, M, cz);
     return cudaGetLastError();
 }
 

@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256) pipe(double* out, double a, double b, int
         if (OP == 2) { x0 = x0 * b; x1 = x1 * b; x2 = x2 * b; x3 = x3 * b; x4 = x4 * b; x5 = x5 * b; x6 = x6 * b; x7 = x7 * b; }
         if (OP == 3) { x0 = a / x0; x1 = a / x1; x2 = a / x2; x3 = a / x3; x4 = a / x4; x5 = a / x5; x6 = a / x6; x7 = a / x7; }
         if (OP == 4) { x0 = fmax(x0, b) + a; x1 = fmax(x1, b) + a; x2 = fmax(x2, b) + a; x3 = fmax(x3, b) + a; x4 = fmax(x4, b) + a; x5 = fmax(x5, b) + a; x6 = fmax(x6, b) + a; x7 = fmax(x7, b) + a; }
+        if (OP == 6) { x0 = (fabs(x0) > fabs(b) ? x0 : b) + a; x1 = (fabs(x1) > fabs(b) ? x1 : b) + a; x2 = (fabs(x2) > fabs(b) ? x2 : b) + a; x3 = (fabs(x3) > fabs(b) ? x3 : b) + a; x4 = (fabs(x4) > fabs(b) ? x4 : b) + a; x5 = (fabs(x5) > fabs(b) ? x5 : b) + a; x6 = (fabs(x6) > fabs(b) ? x6 : b) + a; x7 = (fabs(x7) > fabs(b) ? x7 : b) + a; }
         if (OP == 5) { x0 = sqrt(x0) + a; x1 = sqrt(x1) + a; x2 = sqrt(x2) + a; x3 = sqrt(x3) + a; x4 = sqrt(x4) + a; x5 = sqrt(x5) + a; x6 = sqrt(x6) + a; x7 = sqrt(x7) + a; }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
@@ -43,6 +44,7 @@ int main() {
     run<3>("ddiv (a/x)", d, 1);
     run<4>("fmax+DADD", d, 2);
     run<5>("sqrt+DADD", d, 2);
+    run<6>("(|x|>|b|?x:b)+DADD", d, 2);
     long n = 1L << 28;   // 4 GiB per buffer as double2
     double2 *a, *b; cudaMalloc(&a, n * 16); cudaMalloc(&b, n * 16); cudaMemset(a, 1, n * 16);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
