@@ -364,6 +364,14 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
     const int i = x0 + tx;
     int s0 = 0;        // ring slot of plane z - HAL
     int ab = 0;        // aux buffer of plane z
+    // element offsets of the ring slots of planes z-3 .. z+3 (block-uniform); shifted by one entry per plane
+    int zo[2 * HAL + 1];
+#pragma unroll
+    for (int k = 0; k <= 2 * HAL; ++k) zo[k] = NDIM == 3 ? k * G::PLANE : 0;
+    // output / phi^n addressing: element offset of this thread's nodes in plane z, advanced by vs2 per plane
+    long lin_k[NY];
+#pragma unroll
+    for (int k = 0; k < NY; ++k) lin_k[k] = (long)i + (long)(y0 + ty + k * TY) * vs1 + (long)zbeg * vs2;
 
     for (int z = zbeg; z < zend; ++z) {
         unsigned txb = 0;
@@ -375,10 +383,6 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
             if (txb && leader) mbar_expect_tx(bar, txb);
             cp_async_commit();
         }
-        // element offsets of the ring slots of planes z-3 .. z+3 (block-uniform)
-        int zo[2 * HAL + 1];
-#pragma unroll
-        for (int k = 0; k <= 2 * HAL; ++k) { int sl = s0 + k; sl = sl >= RING ? sl - RING : sl; zo[k] = NDIM == 3 ? sl * G::PLANE : 0; }
         const T* cur = ring + zo[HAL];
         const T* auxz = aux + (size_t)ab * A.n * G::TILE;
 #pragma unroll
@@ -408,7 +412,7 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                     return c0[off];
                 };
                 // coefficient component d of term k (times g(t))
-                auto coef = [&](const TermDev& tm, int kk, int d) -> double {
+                auto coef_gen = [&](const TermDev& tm, int kk, int d, const bool SCALE) -> double {
                     double v;
                     const int ck = COEFK >= 0 ? COEFK : tm.coef_kind;      // compile-time for the single-term advection kernels
                     if (ck == COEF_FIELD) {
@@ -421,9 +425,11 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                         v = (tm.cval[d] * __ldg(tm.tab[d][0] + i)) * __ldg(tm.tab[d][1] + j);
                         if (NDIM == 3) v = v * __ldg(tm.tab[d][2] + z);
                     } else v = tm.cval[d];
-                    if (tm.scaled) v = v * tm.g;
+                    if (SCALE && tm.scaled) v = v * tm.g;
                     return v;
                 };
+                auto coef = [&](const TermDev& tm, int kk, int d) -> double { return coef_gen(tm, kk, d, true); };
+                auto coef_raw = [&](const TermDev& tm, int kk, int d) -> double { return coef_gen(tm, kk, d, false); };
                 // second-order ENO pair along d, undivided: returns h*neg, h*pos (levelsetterms.jl:156-170, 252-265)
                 auto eno2 = [&](int d, double& ng, double& ps) {
                     const T pm2 = at(d, -2), pm1 = at(d, -1), pp1 = at(d, 1), pp2 = at(d, 2);
@@ -448,12 +454,14 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                     double H = 0.0;
                     if ((MASK & M_ADV_WENO) && (ONE || (tm.kind == TERM_ADVECTION && tm.scheme == SCHEME_WENO5))) {
                         // levelsetterms.jl:73-82 : H = sum_d u_d * weno(d) = sum_d (|u_d| / h_d) * W_d, left to right
+                        const double g = tm.scaled ? tm.g : 1.0;
 #pragma unroll
                         for (int d = 0; d < NDIM; ++d) {
-                            const double u = coef(tm, kk, d);
-                            const int s = u > 0 ? 1 : -1;       // upwind-ordered sampling: q_k = phi[i - s*(3-k)]
+                            const double u = coef_raw(tm, kk, d);                 // velocity before the time factor g(t)
+                            // v = u*g; v > 0 selects the minus-biased stencil.  sign(v) = sign(u)*sign(g); |v|/h = |u| * (|g|/h)
+                            const int s = ((u > 0) & (g > 0)) | ((u < 0) & (g < 0)) ? 1 : -1;   // upwind-ordered sampling: q_k = phi[i - s*(3-k)]
                             const double w = weno5_up<T>(up(d, -3, s), up(d, -2, s), up(d, -1, s), qc, up(d, 1, s), up(d, 2, s));
-                            const double a = fabs(u) * ih[d];
+                            const double a = fabs(u) * (fabs(g) * ih[d]);
                             H = d == 0 ? a * w : fma(a, w, H);
                         }
                     } else if ((MASK & M_ADV_UPWIND) && (ONE || tm.kind == TERM_ADVECTION)) {
@@ -527,7 +535,7 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                 } else {
                     for (int kk = 0; kk < P.nterms; ++kk) one_term(P.terms[kk], kk);
                 }
-                const long lin = (long)i + (long)j * vs1 + (long)z * vs2;
+                const long lin = lin_k[k];
                 P.out[lin] = x;
                 if (P.out2) P.out2[lin] = x2;
             }
@@ -538,6 +546,11 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
             __syncthreads();
             s0 = s0 + 1 == RING ? 0 : s0 + 1;
             ab = ab + 1 == G::NBUF ? 0 : ab + 1;
+#pragma unroll
+            for (int k = 0; k < 2 * HAL; ++k) zo[k] = zo[k + 1];
+            { int sl = s0 + 2 * HAL; sl = sl >= RING ? sl - RING : sl; zo[2 * HAL] = sl * G::PLANE; }
+#pragma unroll
+            for (int k = 0; k < NY; ++k) lin_k[k] += vs2;
         }
     }
 }

@@ -173,6 +173,21 @@ def test_strict_kernel_all_terms(m, O, strict, name, case, dtype):
         assert d <= tol * max(1.0, np.abs(a).max()), (name, integ, d)
 
 
+@pytest.mark.parametrize("name,case", [c for c in _small_cases() if not c[0].startswith("1d")],
+                         ids=[c[0] for c in _small_cases() if not c[0].startswith("1d")])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_tiled_kernel_all_terms(m, O, name, case, dtype):
+    """The same matrix through the default kernel selection, i.e. the tiled cp.async/TMA kernels (2-D and 3-D): every
+    term, every BC kind (index-remap and polynomial-extrapolation instantiations), partial tiles on every side, all three
+    integrators.  Tolerance = the BASELINE bar (1e-10 / 1e-4), far above what 8 steps accumulate."""
+    case = H.Case(case.name, case.lc, case.hc, case.n, case.phi0, case.terms, case.bc, dtype)
+    for integ in ("FE", "RK2", "RK3"):
+        a, b, _, n = run_pair(m, O, case, integ=integ, steps=8)
+        tol = 1e-10 if dtype == np.float64 else 1e-4
+        d = np.abs(a.astype(np.float64) - b.astype(np.float64)).max()
+        assert not np.isnan(b).any() and d <= tol * max(1.0, np.abs(a).max()), (name, integ, d)
+
+
 # ------------------------------------------------------------------------------------------------
 # BASELINE.json configs, 100 RK3 steps, default kernel selection (tiled where available)
 # ------------------------------------------------------------------------------------------------
