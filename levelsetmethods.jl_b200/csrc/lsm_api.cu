@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -65,6 +66,10 @@ struct lsm_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;     // pending stage timings
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t ev_user[8] = {};
+    // fused CFL (lsm_integrate only): request for the last stage of the current step, and its pending result
+    struct { bool on = false; double g_next = 0, tau = 0; } fuse_req;
+    struct { bool valid = false; const void* field = nullptr; uint64_t version = 0; double g = 0; } fused;
+    int opt_fuse_cfl = 1;
 };
 
 struct lsm_field {
@@ -108,6 +113,7 @@ int32_t ctx_common_init(lsm_ctx* c) {
     CU(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
     CU(cudaMalloc(&c->d_scalar, 64));
     CU(cudaMallocHost(&c->h_scalar, 64));
+    if (getenv("LSM_B200_NO_FUSE_CFL")) c->opt_fuse_cfl = 0;
     return LSM_OK;
 }
 
@@ -315,6 +321,21 @@ int32_t run_stage_t(lsm_ctx* c, lsm_field* in, lsm_field* p0, lsm_field* out, ls
     for (int d = 0; d < 3; ++d) { P.h[d] = in->h[d]; if (d < in->ndim) dxmin = std::min(dxmin, in->h[d]); }
     P.dxmin = dxmin;
     for (int k = 0; k < nterms; ++k) TRY(make_term_dev(in, terms[k], term_scale(terms[k], tstage, gscale, k), &P.terms[k]));
+    P.cfl_out = nullptr; P.cfl_g = 0; P.cfl_tau = 0;
+    if (c->fuse_req.on) {
+        c->fuse_req.on = false;
+        const TermDev& t0 = P.terms[0];
+        if (nterms == 1 && t0.kind == TERM_ADVECTION && t0.scheme == SCHEME_WENO5 && t0.coef_kind == COEF_FIELD && !t0.coef_f64 &&
+            c->opt_kernel != 1 && in->ndim == 3 && stage_tiled_supported<T>(in->ndim, P)) {
+            bool remap = true;      // the fused variant exists for the index-remap instantiation only
+            for (int d = 0; d < 3; ++d) for (int sd = 0; sd < 2; ++sd) if (P.in.bc[d][sd].kind == BC_EXTRAP && P.in.bc[d][sd].P > 0) remap = false;
+            if (!remap) goto no_fuse;
+            P.cfl_out = c->d_scalar + 1; P.cfl_g = c->fuse_req.g_next; P.cfl_tau = c->fuse_req.tau;
+            CU(cudaMemsetAsync(c->d_scalar + 1, 0, 8, c->stream));
+            c->fused.valid = true; c->fused.field = terms[0].field; c->fused.version = terms[0].field->version; c->fused.g = c->fuse_req.g_next;
+        }
+    no_fuse:;
+    }
 
     const int last = in->ndim - 1, nl = in->n[last];
     if (c->nranks > 1 && !in->halo_valid) {        // e.g. right after an upload
@@ -397,6 +418,21 @@ int32_t cfl_bits(lsm_ctx* ctx, lsm_field* phi, const lsm_term& t, double g, unsi
         for (const auto& e : ctx->cfl_cache)
             if (e.kind == t.kind && e.field == t.field && e.version == t.field->version && e.scaled == td.scaled &&
                 (!td.scaled || e.g == g)) { *bits_out = e.bits; return LSM_OK; }
+    }
+    if (ctx->fused.valid) {
+        ctx->fused.valid = false;
+        if (ctx->fused.field == t.field && ctx->fused.version == t.field->version && td.scaled && ctx->fused.g == g && t.kind == LSM_TERM_ADVECTION) {
+            if (ctx->nranks > 1) NC(nccl().AllReduce(ctx->d_scalar + 1, ctx->d_scalar + 1, 1, ncclUint64, ncclMax, ctx->nccl_comm, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->h_scalar + 1, ctx->d_scalar + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            ctx->cnt.d2h_bytes += 8;
+            if (ctx->h_scalar[1] != 0ULL) {      // a candidate was found (always, see StageParams::cfl_tau); else fall through to the full pass
+                *bits_out = ctx->h_scalar[1];
+                for (auto& en : ctx->cfl_cache)
+                    if (en.kind == t.kind && en.field == t.field) en = {t.kind, t.field, t.field->version, g, td.scaled, *bits_out};
+                return LSM_OK;
+            }
+        }
     }
     CflParams P{};
     P.term = td;
@@ -563,6 +599,7 @@ int32_t lsm_set_option(lsm_ctx* c, int32_t option, int32_t value) {
         case LSM_OPT_TIME_STAGES: c->opt_time = value != 0; break;
         case LSM_OPT_CFL_CACHE: c->opt_cfl_cache = value != 0; c->cfl_cache.clear(); break;
         case LSM_OPT_OVERLAP: c->opt_overlap = value != 0; break;
+        case LSM_OPT_FUSE_CFL: c->opt_fuse_cfl = value != 0; break;
         default: return fail(LSM_ERR_ARG, "unknown option %d", option);
     }
     return LSM_OK;
@@ -844,8 +881,19 @@ int32_t lsm_integrate(lsm_ctx* ctx, int32_t integrator, double cfl, lsm_field* p
         rc = compute_cfl_impl(ctx, phi, terms, nterms, tc, nullptr, &dt_cfl);
         if (rc != LSM_OK) { finished = false; break; }
         const double dt = jl_min(jl_min(dt_max, cfl * dt_cfl), tf - tc);   // timestepping.jl:111
-        for (int s = 1; s <= nstages(integrator) && rc == LSM_OK; ++s)
+        for (int s = 1; s <= nstages(integrator) && rc == LSM_OK; ++s) {
+            if (s == nstages(integrator) && ctx->opt_fuse_cfl && ctx->opt_cfl_cache && nterms == 1 && terms[0].kind == LSM_TERM_ADVECTION &&
+                terms[0].coef_kind == LSM_COEF_FIELD && terms[0].tscale_kind == LSM_TS_COS && (tc + dt) <= tf - jl_eps(tc + dt)) {
+                // next step's CFL maximum from this stage's velocity traffic: max(g') >= (1 - 1e-13) * max(g) * |g'/g|
+                for (const auto& en : ctx->cfl_cache)
+                    if (en.kind == terms[0].kind && en.field == terms[0].field && en.version == terms[0].field->version && en.scaled && en.g != 0.0) {
+                        const double gn = term_scale(terms[0], tc + dt, nullptr, 0);
+                        ctx->fuse_req.on = true; ctx->fuse_req.g_next = gn;
+                        ctx->fuse_req.tau = (1.0 - 1e-13) * bits_to_double(en.bits) * std::fabs(gn / en.g);
+                    }
+            }
             rc = stage_impl(ctx, integrator, s, phi, terms, nterms, tc, dt, nullptr);
+        }
         if (rc != LSM_OK) { finished = false; break; }
         tc += dt;
         ++steps;

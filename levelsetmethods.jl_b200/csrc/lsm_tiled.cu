@@ -228,7 +228,7 @@ __device__ __forceinline__ int remap_index(int i, int n, int kind_lo, int kind_h
 // Fused stage kernel.  MASK = which term kinds the instantiation carries code for; the terms themselves
 // (order, coefficients) are runtime data, applied one after the other like the reference
 // (x = base; x -= c*H_1; x -= c*H_2; ..., timestepping.jl:128-202).
-template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, int TX, int TY, int NY, int MINB>
+template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL, int TX, int TY, int NY, int MINB>
 __global__ void __launch_bounds__(TX * TY, MINB)
 stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ AuxList A, const __grid_constant__ TmaMaps M, const int cz) {
     using G = TileGeom<T, NDIM, TX, TY, NY>;
@@ -362,6 +362,8 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
 
     const double ih[3] = {1.0 / P.h[0], 1.0 / P.h[1], NDIM == 3 ? 1.0 / P.h[2] : 0.0};
     const int i = x0 + tx;
+    unsigned long long cfl_best = 0ULL;                       // fused CFL: this thread's exact maximum (IEEE bits)
+    constexpr bool do_cfl = FCFL;        // separate instantiation: the lean kernel carries none of this code
     int s0 = 0;        // ring slot of plane z - HAL
     int ab = 0;        // aux buffer of plane z
     // element offsets of the ring slots of planes z-3 .. z+3 (block-uniform); shifted by one entry per plane
@@ -455,14 +457,27 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                     if ((MASK & M_ADV_WENO) && (ONE || (tm.kind == TERM_ADVECTION && tm.scheme == SCHEME_WENO5))) {
                         // levelsetterms.jl:73-82 : H = sum_d u_d * weno(d) = sum_d (|u_d| / h_d) * W_d, left to right
                         const double g = tm.scaled ? tm.g : 1.0;
+                        double uu[3] = {0, 0, 0}, sest = 0.0;
 #pragma unroll
                         for (int d = 0; d < NDIM; ++d) {
                             const double u = coef_raw(tm, kk, d);                 // velocity before the time factor g(t)
+                            if (do_cfl) { uu[d] = u; sest = fma(fabs(u), fabs(P.cfl_g) * ih[d], sest); }
                             // v = u*g; v > 0 selects the minus-biased stencil.  sign(v) = sign(u)*sign(g); |v|/h = |u| * (|g|/h)
                             const int s = ((u > 0) & (g > 0)) | ((u < 0) & (g < 0)) ? 1 : -1;   // upwind-ordered sampling: q_k = phi[i - s*(3-k)]
                             const double w = weno5_up<T>(up(d, -3, s), up(d, -2, s), up(d, -1, s), qc, up(d, 1, s), up(d, 2, s));
                             const double a = fabs(u) * (fabs(g) * ih[d]);
                             H = d == 0 ? a * w : fma(a, w, H);
+                        }
+                        if (do_cfl && !(sest < P.cfl_tau)) {
+                            // candidate for the maximum: the reference expression, bit for bit (levelsetterms.jl:90-96)
+                            double sx = 0.0;
+#pragma unroll
+                            for (int d = 0; d < NDIM; ++d) {
+                                const double q = __ddiv_rn(fabs(__dmul_rn(uu[d], P.cfl_g)), P.h[d]);
+                                sx = d == 0 ? q : __dadd_rn(sx, q);
+                            }
+                            const unsigned long long bits = isnan(sx) ? 0x7FF8000000000000ULL : (unsigned long long)__double_as_longlong(sx);
+                            cfl_best = bits > cfl_best ? bits : cfl_best;
                         }
                     } else if ((MASK & M_ADV_UPWIND) && (ONE || tm.kind == TERM_ADVECTION)) {
 #pragma unroll
@@ -553,6 +568,14 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
             for (int k = 0; k < NY; ++k) lin_k[k] += vs2;
         }
     }
+    if (do_cfl) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, cfl_best, o);
+            cfl_best = other > cfl_best ? other : cfl_best;
+        }
+        if (lane == 0 && cfl_best) atomicMax(P.cfl_out, cfl_best);
+    }
 }
 
 #ifndef LSM_TX
@@ -592,11 +615,11 @@ bool encode_map3(CUtensorMap* m, const void* base, long n0, long n1, long nplane
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP>
+template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL = false>
 cudaError_t launch_tiled(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
     constexpr int TX = LSM_TX, TY = LSM_TY, NY = LSM_NY;
     using G = TileGeom<T, NDIM, TX, TY, NY>;
-    auto kern = stage_tiled_kernel<T, NDIM, MASK, NTS, COEFK, REMAP, TX, TY, NY, LSM_MINB>;
+    auto kern = stage_tiled_kernel<T, NDIM, MASK, NTS, COEFK, REMAP, FCFL, TX, TY, NY, LSM_MINB>;
     const size_t smem = G::smem_bytes(A.n);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
@@ -636,7 +659,10 @@ cudaError_t launch_by_mask(int mask, const StageParams<T>& P, const AuxList& A, 
             case M_ADV_WENO:
                 if (P.nterms == 1) {
                     const TermDev& t0 = P.terms[0];
-                    if (t0.coef_kind == COEF_FIELD && A.first[0] == 0) return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_FIELD, REMAP>(P, A, s);
+                    if (t0.coef_kind == COEF_FIELD && A.first[0] == 0) {
+                        if (NDIM == 3 && P.cfl_out) return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_FIELD, REMAP, true>(P, A, s);
+                        return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_FIELD, REMAP>(P, A, s);
+                    }
                     if (t0.coef_kind == COEF_SEPARABLE) return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_SEPARABLE, REMAP>(P, A, s);
                     if (t0.coef_kind == COEF_CONST) return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_CONST, REMAP>(P, A, s);
                 }

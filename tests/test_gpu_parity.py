@@ -332,13 +332,22 @@ def test_hooks_update_func_and_incremental(m, O):
 def test_counters_and_launch_accounting(m):
     ctx = m.default_context()
     case = H.c3_enright(32)
-    phi = case.engine_field(m)
-    eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=m.RK3())
-    eq.state.device()
-    eq.terms[0].velocity.base.device()            # upload the coefficient (one AoS->SoA kernel) before counting
-    ctx.reset_counters()
-    m.integrate(eq, 0.02)
-    c = ctx.counters()
-    assert c["stage_launches"] == 3 * eq.steps_taken
-    assert c["cfl_passes"] == eq.steps_taken          # cos(pi t/T) scale changes every step -> one CFL pass per step
-    assert c["kernel_launches"] == c["stage_launches"] + c["cfl_passes"]
+    results = []
+    for fuse in (0, 1):
+        ctx.set_option(m._lib.OPT_FUSE_CFL, fuse)
+        phi = case.engine_field(m)
+        eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=m.RK3())
+        eq.state.device()
+        eq.terms[0].velocity.base.device()            # upload the coefficient (one AoS->SoA kernel) before counting
+        ctx.reset_counters()
+        m.integrate(eq, 0.02)
+        c = ctx.counters()
+        assert c["stage_launches"] == 3 * eq.steps_taken
+        # cos(pi t/T) changes every step: one CFL reduction per step, unless the last RK stage of the previous step
+        # already produced it (fused CFL) — then only the very first step needs a separate pass
+        assert c["cfl_passes"] == (1 if fuse else eq.steps_taken)
+        assert c["kernel_launches"] == c["stage_launches"] + c["cfl_passes"]
+        results.append((eq.t, eq.steps_taken, eq.state.peek().copy()))
+    ctx.set_option(m._lib.OPT_FUSE_CFL, 1)
+    # the fused reduction is exact: identical step sizes, hence bit-identical states
+    assert results[0][:2] == results[1][:2] and np.array_equal(results[0][2], results[1][2])
