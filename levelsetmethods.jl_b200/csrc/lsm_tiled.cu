@@ -108,8 +108,6 @@ __device__ __forceinline__ double absmax5(double a, double b, double c, double d
     m = fabs(e) > fabs(m) ? e : m;
     return m;
 }
-__device__ __forceinline__ double pos_part(double x) { return x > 0.0 ? x : 0.0; }   // levelsetterms.jl:180
-__device__ __forceinline__ double neg_part(double x) { return x < 0.0 ? x : 0.0; }   // levelsetterms.jl:181
 
 // Undivided upwind WENO5: given six samples in upwind order (q3 is the node, q0 the far upwind
 // end), returns h * weno5 of the reference (derivatives.jl:61-121), i.e. the reference value is
@@ -488,30 +486,35 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                             H = d == 0 ? a * der : fma(a, der, H);
                         }
                     } else if ((MASK & (M_NORMAL | M_EIK)) && (ONE || tm.kind == TERM_NORMAL || tm.kind == TERM_EIKONAL)) {
-                        // Godunov |grad phi| from the ENO2 pair, both upwind selections (levelsetterms.jl:156-170, 252-265)
-                        double gp = 0.0, gm = 0.0;
+                        // Godunov |grad phi| from the ENO2 pair (levelsetterms.jl:156-170, 252-265).  Only ONE of the two
+                        // upwind selections is ever used at a node — grad+ when the sign source (speed v, frozen S0, or phi
+                        // itself) is > 0, grad- otherwise — so only that one is accumulated.
+                        double cf = 0.0;                      // v or S0
+                        bool sp;
+                        if (tm.kind == TERM_NORMAL) { cf = coef(tm, kk, 0); sp = cf > 0; }
+                        else if (tm.coef_kind == COEF_NONE) sp = qc > T(0);
+                        else { cf = coef(tm, kk, 0); sp = cf > 0; }
+                        double gsel = 0.0;
 #pragma unroll
                         for (int d = 0; d < NDIM; ++d) {
                             double ng, ps;
                             eno2(d, ng, ps);
-                            const double i2 = ih[d] * ih[d];
-                            const double a = pos_part(ng), b = neg_part(ps), c = neg_part(ng), e = pos_part(ps);
-                            gp = fma(fma(a, a, b * b), i2, gp);
-                            gm = fma(fma(c, c, e * e), i2, gm);
+                            // grad+: positive(neg)^2 + negative(pos)^2 ; grad-: negative(neg)^2 + positive(pos)^2
+                            const double a = ((ng > 0) == sp) ? ng : 0.0;
+                            const double b = ((ps < 0) == sp) ? ps : 0.0;
+                            gsel = fma(fma(a, a, b * b), ih[d] * ih[d], gsel);
                         }
+                        const double nrm = sqrt(gsel);
                         if (tm.kind == TERM_NORMAL) {
-                            const double v = coef(tm, kk, 0);
                             // positive(v)*sqrt(grad+) + negative(v)*sqrt(grad-): one of the two products is exactly 0
                             // (a NaN speed gives 0 like positive()/negative() do)
-                            H = (v > 0 ? v : (v < 0 ? v : 0.0)) * sqrt(v > 0 ? gp : gm);
+                            H = (cf > 0 ? cf : (cf < 0 ? cf : 0.0)) * nrm;
                         } else if (tm.coef_kind == COEF_NONE) {          // live sign, O&F 7.6 (levelsetterms.jl:237-242)
-                            const double nrm = sqrt(qc > T(0) ? gp : gm);
                             const double den = sqrt(double(T(qc * qc)) + (nrm * nrm) * (P.dxmin * P.dxmin));
                             const double S = den == 0.0 ? 0.0 : double(qc) / den;
                             H = S * (nrm - 1.0);
                         } else {                                         // frozen sign, O&F 7.5 (levelsetterms.jl:243-247)
-                            const double S0 = coef(tm, kk, 0);
-                            H = S0 * (sqrt(S0 > 0 ? gp : gm) - 1.0);
+                            H = cf * (nrm - 1.0);
                         }
                     } else if ((MASK & M_CURV) && (ONE || tm.kind == TERM_CURVATURE)) {
                         // levelsetterms.jl:111-121 + levelsetops.jl:197-244:  b * kappa * |grad phi| = b * (tr(H) q - g'Hg) / q
