@@ -325,7 +325,7 @@ int32_t run_stage_t(lsm_ctx* c, lsm_field* in, lsm_field* p0, lsm_field* out, ls
     if (c->fuse_req.on) {
         c->fuse_req.on = false;
         const TermDev& t0 = P.terms[0];
-        if (nterms == 1 && t0.kind == TERM_ADVECTION && t0.scheme == SCHEME_WENO5 && t0.coef_kind == COEF_FIELD && !t0.coef_f64 &&
+        if (nterms == 1 && t0.kind == TERM_ADVECTION && t0.scheme == SCHEME_WENO5 && (t0.coef_kind == COEF_SEPARABLE || (t0.coef_kind == COEF_FIELD && !t0.coef_f64)) &&
             c->opt_kernel != 1 && in->ndim == 3 && stage_tiled_supported<T>(in->ndim, P)) {
             bool remap = true;      // the fused variant exists for the index-remap instantiation only
             for (int d = 0; d < 3; ++d) for (int sd = 0; sd < 2; ++sd) if (P.in.bc[d][sd].kind == BC_EXTRAP && P.in.bc[d][sd].P > 0) remap = false;
@@ -414,7 +414,7 @@ int nstages(int integ) { return integ == LSM_FORWARD_EULER ? 1 : integ == LSM_RK
 int32_t cfl_bits(lsm_ctx* ctx, lsm_field* phi, const lsm_term& t, double g, unsigned long long* bits_out) {
     TermDev td;
     TRY(make_term_dev(phi, t, g, &td));
-    if (ctx->opt_cfl_cache && t.coef_kind == LSM_COEF_FIELD) {
+    if (ctx->opt_cfl_cache && (t.coef_kind == LSM_COEF_FIELD || t.coef_kind == LSM_COEF_SEPARABLE)) {
         for (const auto& e : ctx->cfl_cache)
             if (e.kind == t.kind && e.field == t.field && e.version == t.field->version && e.scaled == td.scaled &&
                 (!td.scaled || e.g == g)) { *bits_out = e.bits; return LSM_OK; }
@@ -447,7 +447,7 @@ int32_t cfl_bits(lsm_ctx* ctx, lsm_field* phi, const lsm_term& t, double g, unsi
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->cnt.d2h_bytes += 8;
     *bits_out = *ctx->h_scalar;
-    if (ctx->opt_cfl_cache && t.coef_kind == LSM_COEF_FIELD) {
+    if (ctx->opt_cfl_cache && (t.coef_kind == LSM_COEF_FIELD || t.coef_kind == LSM_COEF_SEPARABLE)) {
         bool replaced = false;
         for (auto& en : ctx->cfl_cache)
             if (en.kind == t.kind && en.field == t.field) { en = {t.kind, t.field, t.field->version, g, td.scaled, *bits_out}; replaced = true; }
@@ -883,7 +883,7 @@ int32_t lsm_integrate(lsm_ctx* ctx, int32_t integrator, double cfl, lsm_field* p
         const double dt = jl_min(jl_min(dt_max, cfl * dt_cfl), tf - tc);   // timestepping.jl:111
         for (int s = 1; s <= nstages(integrator) && rc == LSM_OK; ++s) {
             if (s == nstages(integrator) && ctx->opt_fuse_cfl && ctx->opt_cfl_cache && nterms == 1 && terms[0].kind == LSM_TERM_ADVECTION &&
-                terms[0].coef_kind == LSM_COEF_FIELD && terms[0].tscale_kind == LSM_TS_COS && (tc + dt) <= tf - jl_eps(tc + dt)) {
+                (terms[0].coef_kind == LSM_COEF_FIELD || terms[0].coef_kind == LSM_COEF_SEPARABLE) && terms[0].tscale_kind == LSM_TS_COS && (tc + dt) <= tf - jl_eps(tc + dt)) {
                 // next step's CFL maximum from this stage's velocity traffic: max(g') >= (1 - 1e-13) * max(g) * |g'/g|
                 for (const auto& en : ctx->cfl_cache)
                     if (en.kind == terms[0].kind && en.field == terms[0].field && en.version == terms[0].field->version && en.scaled && en.g != 0.0) {

@@ -38,6 +38,9 @@ namespace lsm {
 
 namespace {
 
+#ifndef LSM_MINB_2D
+#define LSM_MINB_2D 4      // 2-D blocks process a single tile (load, wait, compute): latency bound, so favour resident blocks
+#endif
 constexpr int HAL = 3;           // WENO5 reach; every term's stencil fits in it
 
 enum : int { M_ADV_WENO = 1, M_ADV_UPWIND = 2, M_NORMAL = 4, M_CURV = 8, M_EIK = 16, M_ALL = 31 };
@@ -227,7 +230,7 @@ __device__ __forceinline__ int remap_index(int i, int n, int kind_lo, int kind_h
 // (order, coefficients) are runtime data, applied one after the other like the reference
 // (x = base; x -= c*H_1; x -= c*H_2; ..., timestepping.jl:128-202).
 template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL, int TX, int TY, int NY, int MINB>
-__global__ void __launch_bounds__(TX * TY, MINB)
+__global__ void __launch_bounds__(TX * TY, (NDIM == 2 ? LSM_MINB_2D : MINB))
 stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ AuxList A, const __grid_constant__ TmaMaps M, const int cz) {
     using G = TileGeom<T, NDIM, TX, TY, NY>;
     constexpr int RING = G::RING;
@@ -360,6 +363,17 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
 
     const double ih[3] = {1.0 / P.h[0], 1.0 / P.h[1], NDIM == 3 ? 1.0 / P.h[2] : 0.0};
     const int i = x0 + tx;
+    // separable velocity u_d = ((s_d X_d[i]) Y_d[j]) Z_d[z] (single-term advection kernels): the x-y factor is a per-thread
+    // loop invariant, the z factor is block-uniform — same product order as the reference-side tables, so bit-identical
+    double pxy[NY][3];
+    if (COEFK == COEF_SEPARABLE) {
+#pragma unroll
+        for (int k = 0; k < NY; ++k) {
+            const int jj = min(y0 + ty + k * TY, n1 - 1), ii = min(i, n0 - 1);
+#pragma unroll
+            for (int d = 0; d < NDIM; ++d) pxy[k][d] = (P.terms[0].cval[d] * __ldg(P.terms[0].tab[d][0] + ii)) * __ldg(P.terms[0].tab[d][1] + jj);
+        }
+    }
     unsigned long long cfl_best = 0ULL;                       // fused CFL: this thread's exact maximum (IEEE bits)
     constexpr bool do_cfl = FCFL;        // separate instantiation: the lean kernel carries none of this code
     int s0 = 0;        // ring slot of plane z - HAL
@@ -421,6 +435,9 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                             const long node = (long)i + (long)j * vs1 + (long)z * vs2;
                             v = static_cast<const double*>(tm.coef)[(long)d * tm.cstride + node];
                         }
+                    } else if (COEFK == COEF_SEPARABLE) {
+                        v = pxy[k][d];
+                        if (NDIM == 3) v = v * __ldg(tm.tab[d][2] + z);
                     } else if (ck == COEF_SEPARABLE) {
                         v = (tm.cval[d] * __ldg(tm.tab[d][0] + i)) * __ldg(tm.tab[d][1] + j);
                         if (NDIM == 3) v = v * __ldg(tm.tab[d][2] + z);
@@ -581,6 +598,9 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
     }
 }
 
+#ifndef LSM_MINB_2D
+#define LSM_MINB_2D 4      // 2-D blocks process a single tile (load, wait, compute): latency bound, so favour resident blocks
+#endif
 #ifndef LSM_TX
 #define LSM_TX 32
 #define LSM_TY 8
@@ -666,7 +686,10 @@ cudaError_t launch_by_mask(int mask, const StageParams<T>& P, const AuxList& A, 
                         if (NDIM == 3 && P.cfl_out) return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_FIELD, REMAP, true>(P, A, s);
                         return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_FIELD, REMAP>(P, A, s);
                     }
-                    if (t0.coef_kind == COEF_SEPARABLE) return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_SEPARABLE, REMAP>(P, A, s);
+                    if (t0.coef_kind == COEF_SEPARABLE) {
+                        if (NDIM == 3 && P.cfl_out) return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_SEPARABLE, REMAP, true>(P, A, s);
+                        return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_SEPARABLE, REMAP>(P, A, s);
+                    }
                     if (t0.coef_kind == COEF_CONST) return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_CONST, REMAP>(P, A, s);
                 }
                 break;
