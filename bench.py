@@ -40,6 +40,23 @@ B_ALG = 136.0          # bytes per cell-update, 3-D f64 RK3 advection with a sto
 CPU_SAMPLE_N = 96      # the CPU legs run the same configuration on a 96^3 grid (bounded sample)
 
 
+def c5_slab(n, z_first, nz_loc):
+    """BASELINE.json configs[4] "C5" on a slab of the n^3 grid on (-1,-1,-1)..(1,1,1): phi0 = |x - (0.3,0,0)| - 0.4,
+    NormalMotionTerm(v = 0.2 stored scalar field) + AdvectionTerm(u = (-y, x, 0) stored field)."""
+    h = 2.0 / (n - 1)
+    x = (-1.0 + np.arange(n) * h).reshape(n, 1, 1)
+    y = (-1.0 + np.arange(n) * h).reshape(1, n, 1)
+    z = (-1.0 + (np.arange(nz_loc) + z_first) * h).reshape(1, 1, nz_loc)
+    phi = np.empty((n, n, nz_loc), order="F")
+    np.sqrt((x - 0.3) ** 2 + y * y + z * z, out=phi)
+    phi -= 0.4
+    u = np.zeros((3, n, n, nz_loc), order="F")
+    u[0] = -y
+    u[1] = x
+    v = np.full((n, n, nz_loc), 0.2, order="F")
+    return phi, u, v
+
+
 def enright_slab(n, nz_glob, z_first, nz_loc, lz):
     """phi0 and the stored velocity of C3 on a slab [z_first, z_first+nz_loc) of an n x n x nz_glob grid on
     (0,0,0)..(1,1,lz).  Velocity components are rank-1 products ((s*X)*Y)*Z (tests/helpers.py)."""
@@ -160,7 +177,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=512, help="nodes per axis per GPU")
+    ap.add_argument("--n", type=int, default=0, help="nodes per axis (c3: per GPU, default 512; c5: global, default 1024)")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
+                    help="c3 = headline (weak-scaled Enright advection); c5 = BASELINE configs[4], strong-scaled 1024^3 normal motion + advection")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 strict generic, 2 tiled")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -189,19 +208,34 @@ def main():
     m.set_default_context(ctx)
     ctx.set_option(m._lib.OPT_KERNEL, args.kernel)
 
-    n, G = args.n, world
-    nz = n * G
-    lz = float(G)
-    grid = m.CartesianGrid((0, 0, 0), (1, 1, lz), (n, n, nz))
-    z_first, nz_loc = ctx.slab(nz) if G > 1 else (0, nz)
-    phi0, u = enright_slab(n, nz, z_first, nz_loc, lz)
+    G = world
+    c5 = args.workload == "c5"
+    n = args.n or (1024 if c5 else 512)
+    if c5:
+        nz = n
+        grid = m.CartesianGrid((-1, -1, -1), (1, 1, 1), (n, n, nz))
+        z_first, nz_loc = ctx.slab(nz) if G > 1 else (0, nz)
+        phi0, u, v = c5_slab(n, z_first, nz_loc)
+        phi = m.MeshField(phi0, grid, bc=m.NeumannBC(), ctx=ctx)
+        vel = m.MeshField(u, grid, ctx=ctx)
+        spd = m.MeshField(v, grid, ctx=ctx)
+        del u, v
+        terms = (m.NormalMotionTerm(spd), m.AdvectionTerm(vel, m.WENO5()))
+        args.no_e2e = True
+        args.no_cpu = True
+    else:
+        nz = n * G
+        lz = float(G)
+        grid = m.CartesianGrid((0, 0, 0), (1, 1, lz), (n, n, nz))
+        z_first, nz_loc = ctx.slab(nz) if G > 1 else (0, nz)
+        phi0, u = enright_slab(n, nz, z_first, nz_loc, lz)
+        phi = m.MeshField(phi0, grid, bc=m.NeumannBC(), ctx=ctx)
+        vel = m.MeshField(u, grid, ctx=ctx)
+        del u
+        terms = (m.AdvectionTerm(m.TimeScaled(vel, ("cos", PERIOD)), m.WENO5()),)
     nodes_total = n * n * nz
-
-    phi = m.MeshField(phi0, grid, bc=m.NeumannBC(), ctx=ctx)
-    vel = m.MeshField(u, grid, ctx=ctx)
-    del u
-    term = m.AdvectionTerm(m.TimeScaled(vel, ("cos", PERIOD)), m.WENO5())
-    eq = m.LevelSetEquation(terms=(term,), ic=phi, integrator=m.RK3())
+    balg = 160.0 if c5 else B_ALG
+    eq = m.LevelSetEquation(terms=terms, ic=phi, integrator=m.RK3())
     state = eq.state
     lib, L = m._lib.lib(), m._lib
     import ctypes as C
@@ -210,7 +244,7 @@ def main():
 
     def steps_on_device(k, t0):
         t_out, st = C.c_double(), C.c_int64()
-        L.check(lib.lsm_integrate(ctx.handle, L.RK3, 0.5, dev, low.arr, 1, t0, 1e9, float("inf"), k, C.byref(t_out), C.byref(st)))
+        L.check(lib.lsm_integrate(ctx.handle, L.RK3, 0.5, dev, low.arr, len(eq.terms), t0, 1e9, float("inf"), k, C.byref(t_out), C.byref(st)))
         assert st.value == k
         return t_out.value
 
@@ -253,7 +287,7 @@ def main():
         state.vals                               # mark host as the fresh copy -> integrate! uploads it
         dev2 = state.device()                    # H2D of phi (pinned)
         t_out, st = C.c_double(), C.c_int64()
-        L.check(lib.lsm_integrate(ctx.handle, L.RK3, 0.5, dev2, low.arr, 1, 0.0, 1e9, float("inf"), args.steps, C.byref(t_out), C.byref(st)))
+        L.check(lib.lsm_integrate(ctx.handle, L.RK3, 0.5, dev2, low.arr, len(eq.terms), 0.0, 1e9, float("inf"), args.steps, C.byref(t_out), C.byref(st)))
         state._mark_device_advanced()
         res = state.peek()                       # D2H of phi (pinned)
         chk = float(res[0, 0, 0])
@@ -276,14 +310,16 @@ def main():
 
     peak, peak_src = hbm_peak()
     stage_ms = cnt["sum_stage_ms"] / max(cnt["timed_stages"], 1)
-    bytes_per_launch = (B_ALG / 3.0) * (n * n * nz_loc)          # average over the 3 stage launches of a step (40+48+48 B/node)
+    bytes_per_launch = (balg / 3.0) * (n * n * nz_loc)           # average over the 3 stage launches of a step (c3: 40+48+48 B/node)
     achieved = bytes_per_launch / (stage_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if c5 else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C3 Enright sphere {n}x{n}x{nz} (BASELINE.json configs[2]; {n}^3 per GPU), WENO5 + TVD-RK3, NeumannBC, "
-                               "stored Float64 velocity field x cos(pi t/3), CFL reduction every step",
+        "config": {"workload": (f"C5 NormalMotionTerm(v field) + AdvectionTerm(u field), {n}^3 global (BASELINE.json configs[4]), WENO5 + TVD-RK3, "
+                                "NeumannBC, slab-decomposed with NCCL halo exchange" if c5 else
+                                f"C3 Enright sphere {n}x{n}x{nz} (BASELINE.json configs[2]; {n}^3 per GPU), WENO5 + TVD-RK3, NeumannBC, "
+                                "stored Float64 velocity field x cos(pi t/3), CFL reduction every step (fused into the last RK stage)"),
                    "grid": [n, n, nz], "parallelism": f"slab{G}" if G > 1 else "single",
                    "l2": "inputs larger than L2 (each field >= 1 GB per GPU)", "kernel": ["auto", "strict-generic", "tiled"][args.kernel]},
         "clocks": clocks,
