@@ -225,6 +225,57 @@ def test_strict_and_default_kernels_agree(m, O, strict):
 
 
 # ------------------------------------------------------------------------------------------------
+# BASELINE.json's FULL sizes, through size-independent properties (the oracle would need minutes per step there)
+# ------------------------------------------------------------------------------------------------
+def test_full_size_linear_field_is_advected_exactly(m):
+    """512^3 Float64: WENO5 differentiates a linear field exactly (all smoothness indicators vanish) and
+    LinearExtrapolationBC continues it exactly, so phi(x, t) = phi0(x) - t * (u . grad phi0) up to rounding."""
+    n = 512
+    g = m.CartesianGrid((0, 0, 0), (1, 1, 1), (n, n, n))
+    a, u, c = (0.3, -0.2, 0.5), (0.7, -0.4, 0.5), 0.1
+    phi = m.MeshField(lambda x: a[0] * x[0] + a[1] * x[1] + a[2] * x[2] + c, g)
+    eq = m.LevelSetEquation(terms=(m.AdvectionTerm(u),), ic=phi, bc=m.LinearExtrapolationBC(), integrator=m.RK3())
+    h = g.meshsize(1)
+    tf = 12 * 0.5 / (sum(abs(v) for v in u) / h) * (1 - 1e-12)
+    m.integrate(eq, tf)
+    assert eq.steps_taken == 12
+    x, y, z = g.coords()
+    exact = a[0] * x + a[1] * y + a[2] * z + c - tf * sum(ai * ui for ai, ui in zip(a, u))
+    assert np.abs(eq.state.peek() - exact).max() <= 1e-12
+
+
+def test_full_size_flat_field_is_a_fixed_point(m):
+    """512^3 Float32 under the Enright velocity: every difference of a constant field is zero, the epsilon floor keeps
+    the WENO weights finite, so the field must stay bit-identical (test-levelsetterms.jl:53-77 at scale)."""
+    case = H.c3_enright(512, np.float32)
+    case.phi0[...] = 1.0
+    phi = case.engine_field(m)
+    eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=m.RK3())
+    m.integrate(eq, 3 * 0.5 * m.compute_cfl(eq.terms, eq.state, 0.0))
+    out = eq.state.peek()
+    assert eq.steps_taken >= 3 and np.all(out == np.float32(1.0))
+
+
+def test_full_size_strict_and_tiled_kernels_agree(m):
+    """256^3 Float64 C3 and C5: the reference-ordered strict kernel and the restructured tiled kernels (TMA fill, fused
+    CFL, one reciprocal ...) must agree far inside the 1e-10 bar, with identical step sizes."""
+    ctx = m.default_context()
+    for case in (H.c3_enright(256), H.c5_normal_advection(192)):
+        outs = []
+        for kernel in (1, 0):
+            ctx.set_option(OPT_KERNEL, kernel)
+            phi = case.engine_field(m)
+            eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=m.RK3())
+            m.integrate(eq, 3 * 0.5 * m.compute_cfl(eq.terms, eq.state, 0.0) * (1 - 1e-12))
+            outs.append((eq.t, eq.steps_taken, eq.state.peek().copy()))
+        ctx.set_option(OPT_KERNEL, 0)
+        assert outs[0][:2] == outs[1][:2]
+        d = np.abs(outs[0][2] - outs[1][2]).max()
+        assert d <= 1e-13, d
+        assert np.array_equal(np.sign(outs[0][2]), np.sign(outs[1][2]))
+
+
+# ------------------------------------------------------------------------------------------------
 # the reference's own integration tests, run through the engine (test-timestepping.jl, test-levelsetequation.jl)
 # ------------------------------------------------------------------------------------------------
 def _adv_err_1d(m, integ, N, u=1.0, tf=0.5, scheme=None):
