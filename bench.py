@@ -194,9 +194,9 @@ def main():
         return
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    # stdout carries exactly ONE JSON line: keep NCCL's version banner (printed to stdout at NCCL_DEBUG >= VERSION) out of it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO", "TRACE") and not os.environ.get("LSM_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly ONE JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG >= VERSION (WARN included),
+    # so send NCCL's debug output to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
     import lsm_b200 as m
     dist = None

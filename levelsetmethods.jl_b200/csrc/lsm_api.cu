@@ -55,8 +55,8 @@ struct CflCacheEntry { int kind; const void* field; uint64_t version; double g; 
 
 struct lsm_ctx {
     int device = 0, rank = 0, nranks = 1, sm_count = 148;
-    cudaStream_t stream = nullptr, comm = nullptr;
-    cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
+    cudaStream_t stream = nullptr, comm = nullptr, bstream = nullptr;     // compute, halo traffic, boundary slabs (high priority)
+    cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr, ev_main = nullptr;
     ncclComm_t nccl_comm = nullptr;
     unsigned long long* d_scalar = nullptr;     // device scalar for reductions
     unsigned long long* h_scalar = nullptr;     // pinned
@@ -109,6 +109,8 @@ int32_t ctx_common_init(lsm_ctx* c) {
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->comm, cudaStreamNonBlocking));
+    { int lo = 0, hi = 0; CU(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CU(cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, hi)); }
+    CU(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_boundary, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
     CU(cudaMalloc(&c->d_scalar, 64));
@@ -294,13 +296,14 @@ void resolve_timings(lsm_ctx* c) {
 }
 
 template <class T>
-int32_t launch_stage_range(lsm_ctx* c, int ndim, StageParams<T>& P, int r0, int r1) {
+int32_t launch_stage_range(lsm_ctx* c, int ndim, StageParams<T>& P, int r0, int r1, cudaStream_t st = nullptr) {
+    if (!st) st = c->stream;
     if (r1 <= r0) return LSM_OK;
     P.r0 = r0; P.r1 = r1;
     cudaError_t e = cudaErrorNotSupported;
-    if (c->opt_kernel != 1 && stage_tiled_supported<T>(ndim, P)) e = launch_stage_tiled<T>(ndim, P, c->sm_count, c->stream);
+    if (c->opt_kernel != 1 && stage_tiled_supported<T>(ndim, P)) e = launch_stage_tiled<T>(ndim, P, c->sm_count, st);
     else if (c->opt_kernel == 2) return fail(LSM_ERR_UNSUPPORTED, "tiled kernel forced but this configuration is not covered");
-    if (e == cudaErrorNotSupported) e = launch_stage_generic<T>(ndim, P, c->stream);
+    if (e == cudaErrorNotSupported) e = launch_stage_generic<T>(ndim, P, st);
     if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "stage kernel launch failed: %s", cudaGetErrorString(e));
     c->cnt.kernel_launches += 1; c->cnt.stage_launches += 1;
     return LSM_OK;
@@ -344,14 +347,19 @@ int32_t run_stage_t(lsm_ctx* c, lsm_field* in, lsm_field* p0, lsm_field* out, ls
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (c->opt_time) { t0 = pool_event(c); t1 = pool_event(c); cudaEventRecord(t0, c->stream); }
     if (c->nranks > 1 && out_needs_halo && c->opt_overlap && nl >= 4 * HALO) {
-        // boundary slabs first, then ship them while the interior is computed
-        TRY(launch_stage_range<T>(c, in->ndim, P, 0, HALO + 1));
-        TRY(launch_stage_range<T>(c, in->ndim, P, nl - HALO - 1, nl));
-        CU(cudaEventRecord(c->ev_boundary, c->stream));
+        // The two thin boundary slabs run on a high-priority side stream CONCURRENTLY with the interior kernel (their
+        // blocks fill SMs the interior leaves idle at its tail and vice versa); as soon as they are done the comm stream
+        // ships them (NCCL send/recv) while the interior is still being computed.  The next stage waits for both.
+        CU(cudaEventRecord(c->ev_main, c->stream));                 // everything enqueued so far (previous stage, halos, memsets)
+        CU(cudaStreamWaitEvent(c->bstream, c->ev_main, 0));
+        TRY(launch_stage_range<T>(c, in->ndim, P, 0, HALO + 1, c->bstream));
+        TRY(launch_stage_range<T>(c, in->ndim, P, nl - HALO - 1, nl, c->bstream));
+        CU(cudaEventRecord(c->ev_boundary, c->bstream));
         CU(cudaStreamWaitEvent(c->comm, c->ev_boundary, 0));
         TRY(exchange_halo(out, c->comm));
         CU(cudaEventRecord(c->ev_halo, c->comm));
         TRY(launch_stage_range<T>(c, in->ndim, P, HALO + 1, nl - HALO - 1));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_boundary, 0));
         CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
     } else {
         TRY(launch_stage_range<T>(c, in->ndim, P, 0, nl));
@@ -578,6 +586,8 @@ int32_t lsm_ctx_destroy(lsm_ctx* c) {
     if (c->h_scalar) cudaFreeHost(c->h_scalar);
     if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->bstream) cudaStreamDestroy(c->bstream);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->comm) cudaStreamDestroy(c->comm);
     delete c;
