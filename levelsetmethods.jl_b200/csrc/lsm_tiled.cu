@@ -260,8 +260,8 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
     const int kzl = P.in.bc[2][0].kind, kzh = P.in.bc[2][1].kind;
     // TMA fill (one cp.async.bulk.tensor per plane, issued by thread 0, completed on an mbarrier) for tiles that need
     // no ghost resolution; everything else goes through the LDGSTS paths below.
-    const bool tma_phi = NDIM == 3 && (M.enabled == 1 || M.enabled == 2) && xy_in;
-    const bool tma_aux = NDIM == 3 && (M.enabled == 1 || M.enabled == 3) && (x0 + TX <= n0) && (y0 + TY * NY <= n1);
+    const bool tma_phi = NDIM == 3 && M.enabled && xy_in;
+    const bool tma_aux = NDIM == 3 && M.enabled && (x0 + TX <= n0) && (y0 + TY * NY <= n1);
     const bool leader = (tx | ty) == 0;
     unsigned phase = 0;
     if (NDIM == 3 && M.enabled) {
@@ -660,7 +660,6 @@ cudaError_t launch_tiled(const StageParams<T>& P, const AuxList& A, cudaStream_t
         for (int a = 0; ok && a < A.n; ++a)
             ok = ((uintptr_t)A.src[a] % 16 == 0) && encode_map3<T>(&M.aux[a], A.src[a], v.n[0], v.n[1], v.n[2], TX, TY * NY);
         M.enabled = ok ? 1 : 0;
-        if (const char* md = getenv("LSM_B200_TMA_MODE")) M.enabled = ok ? atoi(md) : 0;   // debug: 1 both, 2 phi only, 3 aux only
     }
     dim3 block(TX, TY), grid;
     int cz = 1;
