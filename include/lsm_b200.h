@@ -192,6 +192,14 @@ int32_t lsm_integrate(lsm_ctx* ctx, int32_t integrator, double cfl, lsm_field* p
 /* EikonalReinitializationTerm(phi0) constructor (levelsetterms.jl:217-221): dst = phi0/sqrt(phi0^2+min(h)^2). */
 int32_t lsm_eikonal_s0(lsm_field* dst, const lsm_field* phi0);
 
+/* ---- level-set measures (SURVEY.md §8f "next" row 1): the usual posthook / update_func payload, reduced on the device ---- */
+/* volume(phi) (levelsetops.jl:27-33): prod(h) * sum smooth_heaviside(-phi, min h), all-reduced over ranks. */
+int32_t lsm_volume(lsm_ctx* ctx, lsm_field* phi, double* out);
+/* perimeter(phi) (levelsetops.jl:139-149): prod(h) * sum smooth_delta(phi, min h) * |grad phi| with centred differences; a field
+ * without boundary conditions is given LinearExtrapolationBC like the reference does.  Single-rank contexts, or multi-rank
+ * fields whose ghost planes are current. */
+int32_t lsm_perimeter(lsm_ctx* ctx, lsm_field* phi, double* out);
+
 /* ---- diagnostics (test harness) -------------------------------------------- */
 /* max |a - b| over all owned nodes, all-reduced over ranks. */
 int32_t lsm_max_abs_diff(lsm_ctx* ctx, const lsm_field* a, const lsm_field* b, double* out);

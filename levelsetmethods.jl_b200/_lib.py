@@ -97,6 +97,8 @@ SYMBOLS = {
     "lsm_integrate": (_i32, [_vp, _i32, _dbl, _vp, C.POINTER(lsm_term), _i32, _dbl, _dbl, _dbl, _i64, _pdbl,
                              C.POINTER(_i64)]),
     "lsm_eikonal_s0": (_i32, [_vp, _vp]),
+    "lsm_volume": (_i32, [_vp, _vp, _pdbl]),
+    "lsm_perimeter": (_i32, [_vp, _vp, _pdbl]),
     "lsm_max_abs_diff": (_i32, [_vp, _vp, _vp, _pdbl]),
 }
 

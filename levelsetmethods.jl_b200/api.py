@@ -767,6 +767,22 @@ class LevelSetEquation:
         return f"LevelSetEquation(phi_t + {' + '.join(map(repr, self.terms))} = 0, t={self.t})"
 
 
+def volume(phi) -> float:
+    """``volume(phi)`` (levelsetops.jl:27-33) — measure of {phi <= 0}, reduced on the device (no download of the field)."""
+    phi = current_state(phi)
+    out = C.c_double()
+    L.check(L.lib().lsm_volume(phi._context().handle, phi.device(), C.byref(out)))
+    return out.value
+
+
+def perimeter(phi) -> float:
+    """``perimeter(phi)`` (levelsetops.jl:139-149) — measure of {phi = 0}, reduced on the device."""
+    phi = current_state(phi)
+    out = C.c_double()
+    L.check(L.lib().lsm_perimeter(phi._context().handle, phi.device(), C.byref(out)))
+    return out.value
+
+
 def current_state(eq):
     return eq.state if isinstance(eq, LevelSetEquation) else eq
 

@@ -933,6 +933,41 @@ int32_t lsm_eikonal_s0(lsm_field* dst, const lsm_field* phi0) {
     return LSM_OK;
 }
 
+static int32_t measure_impl(lsm_ctx* ctx, lsm_field* phi, bool perimeter, double* out) {
+    if (!ctx || !phi || !out) return fail(LSM_ERR_ARG, "null argument");
+    if (phi->ctx != ctx || phi->ncomp != 1 || phi->separable) return fail(LSM_ERR_ARG, "volume/perimeter need a real-valued field of this context");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->comm));
+    const int nblocks = ctx->sm_count * 8;
+    double* d_part = nullptr;
+    CU(cudaMalloc(&d_part, sizeof(double) * (size_t)(nblocks + 1)));
+    cudaError_t e;
+    // perimeter reaches off-grid at the border: a field without BCs gets LinearExtrapolationBC (levelsetops.jl:142)
+    lsm_bc saved[3][2];
+    std::memcpy(saved, phi->bc, sizeof saved);
+    const bool had_bc = phi->has_bc;
+    if (perimeter && !had_bc) for (int d = 0; d < phi->ndim; ++d) { phi->bc[d][0] = {LSM_BC_EXTRAP, 1}; phi->bc[d][1] = {LSM_BC_EXTRAP, 1}; }
+    if (perimeter && ctx->nranks > 1 && !phi->halo_valid) {
+        int32_t rc = exchange_halo(phi, ctx->stream);
+        if (rc != LSM_OK) { cudaFree(d_part); return rc; }
+    }
+    if (phi->dtype == LSM_F64) e = launch_measure<double>(phi->ndim, perimeter, make_view<double>(phi), phi->h, d_part, nblocks, d_part + nblocks, ctx->stream);
+    else e = launch_measure<float>(phi->ndim, perimeter, make_view<float>(phi), phi->h, d_part, nblocks, d_part + nblocks, ctx->stream);
+    std::memcpy(phi->bc, saved, sizeof saved);
+    if (e == cudaSuccess && ctx->nranks > 1) {
+        ncclResult_t r = nccl().AllReduce(d_part + nblocks, d_part + nblocks, 1, ncclDouble, ncclSum, ctx->nccl_comm, ctx->stream);
+        if (r != ncclSuccess) { cudaFree(d_part); return fail(LSM_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString(r)); }
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_part + nblocks, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_part);
+    if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "measure kernel failed: %s", cudaGetErrorString(e));
+    ctx->cnt.kernel_launches += 2; ctx->cnt.d2h_bytes += 8;
+    return LSM_OK;
+}
+int32_t lsm_volume(lsm_ctx* ctx, lsm_field* phi, double* out) { return measure_impl(ctx, phi, false, out); }
+int32_t lsm_perimeter(lsm_ctx* ctx, lsm_field* phi, double* out) { return measure_impl(ctx, phi, true, out); }
+
 int32_t lsm_max_abs_diff(lsm_ctx* ctx, const lsm_field* a, const lsm_field* b, double* out) {
     if (!ctx || !a || !b || !out) return fail(LSM_ERR_ARG, "null argument");
     if (a->ctx != ctx || b->ctx != ctx || a->dtype != b->dtype || a->ncomp != 1 || b->ncomp != 1 || a->owned != b->owned)

@@ -506,6 +506,76 @@ cudaError_t launch_getindex(int ndim, const View<T>& v, const int* d_idx, int co
 template cudaError_t launch_getindex<float>(int, const View<float>&, const int*, int, double*, cudaStream_t);
 template cudaError_t launch_getindex<double>(int, const View<double>&, const int*, int, double*, cudaStream_t);
 
+// ---------------------------------------------------------------------------------------------
+// volume / perimeter (levelsetops.jl:27-33, 139-149, smooth_heaviside / smooth_delta :186-195).  Deterministic two-stage
+// sum: per-block partials in a fixed tree, then one block adds the partials in a fixed order.
+// ---------------------------------------------------------------------------------------------
+template <int N, class T, bool PERIM>
+__global__ void __launch_bounds__(256) measure_kernel(const __grid_constant__ View<T> v, const double h0, const double h1, const double h2,
+                                                      const double dmin, double* __restrict__ partials) {
+    const double h[3] = {h0, h1, h2};
+    const long total = (long)v.n[0] * v.n[1] * v.n[2];
+    double acc = 0.0;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i0 = (int)(idx % v.n[0]);
+        const long q = idx / v.n[0];
+        const int i1 = (int)(q % v.n[1]), i2 = (int)(q / v.n[1]);
+        const double x = double(v.p[(long)i0 + (long)i1 * v.s1 + (long)i2 * v.s2]);
+        if (!PERIM) {
+            const double y = -x;
+            double hv;
+            if (y > dmin) hv = 1.0;
+            else if (y < -dmin) hv = 0.0;
+            else hv = 0.5 * (1.0 + y / dmin + 1.0 / M_PI * sin(M_PI * y / dmin));
+            acc += hv;
+        } else if (!(fabs(x) > dmin)) {
+            const double delta = 0.5 / dmin * (1.0 + cos(M_PI * x / dmin));
+            double g2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                const T p = getindex_slow<N, T>(v, i0 + (d == 0), i1 + (d == 1), i2 + (d == 2));
+                const T m = getindex_slow<N, T>(v, i0 - (d == 0), i1 - (d == 1), i2 - (d == 2));
+                const double gd = double(T(p - m)) / (2 * h[d]);
+                g2 = d == 0 ? gd * gd : g2 + gd * gd;
+            }
+            acc += delta * sqrt(g2);
+        }
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256) measure_final_kernel(const double* __restrict__ partials, int n, double scale, double* out) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) acc += partials[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0] * scale;
+}
+template <class T>
+cudaError_t launch_measure(int ndim, bool perimeter, const View<T>& v, const double* h, double* d_partials, int nblocks, double* d_out, cudaStream_t s) {
+    double dmin = h[0], vol = h[0];
+    for (int d = 1; d < ndim; ++d) { dmin = h[d] < dmin ? h[d] : dmin; vol *= h[d]; }
+#define LSM_MEAS(NN) do { if (perimeter) measure_kernel<NN, T, true><<<nblocks, 256, 0, s>>>(v, h[0], h[1], h[2], dmin, d_partials); \
+                          else measure_kernel<NN, T, false><<<nblocks, 256, 0, s>>>(v, h[0], h[1], h[2], dmin, d_partials); } while (0)
+    if (ndim == 1) LSM_MEAS(1); else if (ndim == 2) LSM_MEAS(2); else LSM_MEAS(3);
+#undef LSM_MEAS
+    measure_final_kernel<<<1, 256, 0, s>>>(d_partials, nblocks, vol, d_out);
+    return cudaGetLastError();
+}
+template cudaError_t launch_measure<float>(int, bool, const View<float>&, const double*, double*, int, double*, cudaStream_t);
+template cudaError_t launch_measure<double>(int, bool, const View<double>&, const double*, double*, int, double*, cudaStream_t);
+
 // K6: max |a - b| (bit-pattern max, NaN wins)
 template <class T>
 __global__ void __launch_bounds__(256) max_abs_diff_kernel(const T* __restrict__ a, const T* __restrict__ b, long n, unsigned long long* out) {

@@ -380,6 +380,30 @@ def test_hooks_update_func_and_incremental(m, O):
     assert np.isfinite(eq.state.peek()).all()
 
 
+def test_device_volume_and_perimeter(m, O):
+    """volume / perimeter reduced on the device (levelsetops.jl:27-33,139-149) against the oracle, which
+    reproduces the reference's doctest scalars bit for bit; the parallel sum only changes the summation order."""
+    g = m.CartesianGrid((-1, -1), (1, 1), (200, 200))
+    phi = m.MeshField(lambda x: np.sqrt(x[0] ** 2 + x[1] ** 2) - 0.5, g)           # no BCs: perimeter supplies LinearExtrapolationBC
+    assert m.volume(phi) == pytest.approx(0.7854362890190668, rel=1e-13)           # levelsetops.jl:14-25
+    assert m.perimeter(phi) == pytest.approx(3.1426415491430384, rel=1e-13)        # levelsetops.jl:126-137
+    for case in (H.c3_enright(40), H.c2_zalesak_curvature(96), H.c4_eikonal(24, np.float32)):
+        fo = case.oracle_field()
+        f = case.engine_field(m)
+        assert m.volume(f) == pytest.approx(fo.volume(), rel=1e-12)
+        assert m.perimeter(f) == pytest.approx(fo.perimeter(), rel=1e-12)
+    # as a posthook payload: the state is never downloaded
+    case = H.c1_circle_rotation(64)
+    f = case.engine_field(m)
+    eq = m.LevelSetEquation(terms=case.engine_terms(m, f), ic=f, integrator=m.RK3())
+    vols = []
+    ctx = m.default_context()
+    eq.state.device(); ctx.reset_counters()
+    m.integrate(eq, 0.05, posthook=lambda e: vols.append(m.volume(e)))
+    assert len(vols) == eq.steps_taken and ctx.counters()["d2h_bytes"] < 64 * (len(vols) + 2)
+    assert abs(vols[-1] - vols[0]) < 2e-3 * vols[0]                                # rigid rotation preserves the area
+
+
 def test_counters_and_launch_accounting(m):
     ctx = m.default_context()
     case = H.c3_enright(32)
