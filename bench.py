@@ -257,11 +257,13 @@ def main():
             dist.barrier()
 
     # ---- warm-up, then the device-timed region -------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None      # samples clocks from the warm-up on (all of it is under load)
+    if sampler:
+        time.sleep(0.4)                                       # let nvidia-smi start sampling
     t = steps_on_device(args.warmup, 0.0)
     ctx.set_option(L.OPT_TIME_STAGES, 1)
     barrier()
     ctx.reset_counters()
-    sampler = ClockSampler(local) if rank == 0 else None
     ctx.event_record(0)
     t = steps_on_device(args.steps, t)
     ctx.event_record(1)

@@ -783,6 +783,21 @@ def perimeter(phi) -> float:
     return out.value
 
 
+def eikonal_reinitialize(phi: MeshField, iterations: int = 20, integrator: Optional["TimeIntegrator"] = None, frozen: bool = True):
+    """Device-side alternative to the reference's Newton ``reinitialize!`` (reinitializer.jl:12-42, which stays on the host):
+    `iterations` pseudo-time steps of ``phi_t + sign(phi0)(|grad phi| - 1) = 0`` (EikonalReinitializationTerm, levelsetterms.jl:211-265)
+    applied in place to `phi` — usable as a prehook without leaving the GPU."""
+    if not phi.has_boundary_conditions():
+        raise L.BCError(L.ERR_BC, "reinitialization needs boundary conditions on the field")
+    term = EikonalReinitializationTerm(phi if frozen else None)
+    integ = integrator if integrator is not None else RK2()
+    eq = LevelSetEquation.__new__(LevelSetEquation)
+    eq.terms, eq.integrator, eq.state, eq.t, eq.steps_taken = (term,), integ, phi, 0.0, 0
+    dt = integ.cfl * compute_cfl(eq.terms, phi, 0.0)
+    integrate(eq, dt * iterations * (1 - 1e-12))
+    return phi
+
+
 def current_state(eq):
     return eq.state if isinstance(eq, LevelSetEquation) else eq
 
