@@ -200,6 +200,14 @@ int32_t lsm_volume(lsm_ctx* ctx, lsm_field* phi, double* out);
  * fields whose ghost planes are current. */
 int32_t lsm_perimeter(lsm_ctx* ctx, lsm_field* phi, double* out);
 
+/* extend_along_normals!(F, phi; nb_iters, cfl, frozen, interface_band, min_norm) (velocityextension.jl:20-116, "next" row 2):
+ * nb_iters first-order upwind pseudo-time steps of F_tau + sign(phi) n.grad F = 0 with tau = cfl * min(h).  Runs as ForwardEuler
+ * stages of an upwind AdvectionTerm whose velocity is the signed normal S grad(phi)/|grad(phi)|, zeroed on frozen nodes (which
+ * reproduces the reference's Dirichlet constraint exactly).  frozen: host uint8 mask of this rank's slab (1 = frozen) or NULL
+ * for the band |phi| <= interface_band * min(h).  F and phi must share grid and dtype. */
+int32_t lsm_extend_along_normals(lsm_ctx* ctx, lsm_field* F, lsm_field* phi, int32_t nb_iters, double cfl, const uint8_t* frozen,
+                                 double interface_band, double min_norm);
+
 /* ---- diagnostics (test harness) -------------------------------------------- */
 /* max |a - b| over all owned nodes, all-reduced over ranks. */
 int32_t lsm_max_abs_diff(lsm_ctx* ctx, const lsm_field* a, const lsm_field* b, double* out);

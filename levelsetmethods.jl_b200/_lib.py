@@ -99,6 +99,7 @@ SYMBOLS = {
     "lsm_eikonal_s0": (_i32, [_vp, _vp]),
     "lsm_volume": (_i32, [_vp, _vp, _pdbl]),
     "lsm_perimeter": (_i32, [_vp, _vp, _pdbl]),
+    "lsm_extend_along_normals": (_i32, [_vp, _vp, _vp, _i32, _dbl, _vp, _dbl, _dbl]),
     "lsm_max_abs_diff": (_i32, [_vp, _vp, _vp, _pdbl]),
 }
 

@@ -783,6 +783,31 @@ def perimeter(phi) -> float:
     return out.value
 
 
+def extend_along_normals(F: MeshField, phi: MeshField, nb_iters: int = 50, cfl: float = 0.45, frozen=None,
+                         interface_band: float = 1.5, min_norm: float = 1.0e-14) -> MeshField:
+    """``extend_along_normals!(F, phi; nb_iters, cfl, frozen, interface_band, min_norm)`` (velocityextension.jl:20-78) on the
+    device: extends the speed field `F` off the interface of `phi` along its normals.  Mutates and returns `F`."""
+    if F.mesh.n != phi.mesh.n:
+        raise ValueError("F and phi must be defined on the same mesh")
+    if nb_iters < 0:
+        raise ValueError("nb_iters must be non-negative")
+    if not cfl > 0:
+        raise ValueError("cfl must be strictly positive")
+    fr = None
+    if frozen is not None:
+        fr = frozen.peek() if isinstance(frozen, MeshField) else np.asarray(frozen)
+        if fr.shape != phi.peek().shape:
+            raise ValueError("frozen mask must have the same size as phi")
+        if fr.dtype != np.bool_:
+            raise ValueError("frozen mask must contain Bool values")
+        fr = np.asfortranarray(fr.astype(np.uint8))
+    ctx = phi._context()
+    L.check(L.lib().lsm_extend_along_normals(ctx.handle, F.device(), phi.device(), int(nb_iters), float(cfl),
+                                             None if fr is None else fr.ctypes.data, float(interface_band), float(min_norm)))
+    F._mark_device_advanced()
+    return F
+
+
 def eikonal_reinitialize(phi: MeshField, iterations: int = 20, integrator: Optional["TimeIntegrator"] = None, frozen: bool = True):
     """Device-side alternative to the reference's Newton ``reinitialize!`` (reinitializer.jl:12-42, which stays on the host):
     `iterations` pseudo-time steps of ``phi_t + sign(phi0)(|grad phi| - 1) = 0`` (EikonalReinitializationTerm, levelsetterms.jl:211-265)

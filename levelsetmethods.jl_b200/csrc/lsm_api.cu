@@ -968,6 +968,66 @@ static int32_t measure_impl(lsm_ctx* ctx, lsm_field* phi, bool perimeter, double
 int32_t lsm_volume(lsm_ctx* ctx, lsm_field* phi, double* out) { return measure_impl(ctx, phi, false, out); }
 int32_t lsm_perimeter(lsm_ctx* ctx, lsm_field* phi, double* out) { return measure_impl(ctx, phi, true, out); }
 
+int32_t lsm_extend_along_normals(lsm_ctx* ctx, lsm_field* F, lsm_field* phi, int32_t nb_iters, double cfl, const uint8_t* frozen,
+                                 double interface_band, double min_norm) {
+    if (!ctx || !F || !phi) return fail(LSM_ERR_ARG, "null argument");
+    if (F->ctx != ctx || phi->ctx != ctx || F == phi || F->ncomp != 1 || phi->ncomp != 1 || F->separable || phi->separable)
+        return fail(LSM_ERR_ARG, "F and phi must be distinct scalar fields of this context");
+    if (F->ndim != phi->ndim || F->dtype != phi->dtype) return fail(LSM_ERR_ARG, "F and phi must be defined on the same mesh with the same valtype");
+    for (int d = 0; d < F->ndim; ++d) if (F->nglob[d] != phi->nglob[d]) return fail(LSM_ERR_ARG, "F and phi must have the same size");
+    if (nb_iters < 0) return fail(LSM_ERR_ARG, "nb_iters must be non-negative");
+    if (!(cfl > 0)) return fail(LSM_ERR_ARG, "cfl must be strictly positive");
+    if (interface_band < 0 || min_norm < 0) return fail(LSM_ERR_ARG, "interface_band and min_norm must be non-negative");
+    CU(cudaSetDevice(ctx->device));
+    // boundary conditions: phi's, or LinearExtrapolationBC everywhere (velocityextension.jl:38-43); F gets the same
+    lsm_bc savedP[3][2], savedF[3][2];
+    std::memcpy(savedP, phi->bc, sizeof savedP); std::memcpy(savedF, F->bc, sizeof savedF);
+    const bool hadP = phi->has_bc, hadF = F->has_bc;
+    if (!hadP) for (int d = 0; d < phi->ndim; ++d) { phi->bc[d][0] = {LSM_BC_EXTRAP, 1}; phi->bc[d][1] = {LSM_BC_EXTRAP, 1}; }
+    std::memcpy(F->bc, phi->bc, sizeof savedF);
+    F->has_bc = true; F->halo_valid = false;
+    for (lsm_field* b : {F->buf1, F->buf2}) if (b) { std::memcpy(b->bc, F->bc, sizeof savedF); b->has_bc = true; }
+    auto restore = [&]() {
+        std::memcpy(phi->bc, savedP, sizeof savedP);
+        std::memcpy(F->bc, savedF, sizeof savedF); F->has_bc = hadF; F->halo_valid = false;
+        for (lsm_field* b : {F->buf1, F->buf2}) if (b) { std::memcpy(b->bc, F->bc, sizeof savedF); b->has_bc = hadF; }
+    };
+    lsm_field* vel = nullptr;
+    int32_t rc = field_alloc(ctx, phi->ndim, phi->nglob, phi->dtype, phi->ndim, phi->lc, phi->hc, false, &vel);
+    if (rc != LSM_OK) { restore(); return rc; }
+    unsigned char* d_frozen = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (frozen) {
+        e = cudaMalloc(&d_frozen, (size_t)phi->owned);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_frozen, frozen, (size_t)phi->owned, cudaMemcpyHostToDevice, ctx->stream);
+        ctx->cnt.h2d_bytes += phi->owned;
+    }
+    if (e == cudaSuccess && ctx->nranks > 1 && !phi->halo_valid) { rc = exchange_halo(phi, ctx->stream); }
+    if (e == cudaSuccess && rc == LSM_OK) {
+        e = phi->dtype == LSM_F64
+                ? launch_signed_normals<double>(phi->ndim, make_view<double>(phi), phi->h, min_norm, d_frozen, interface_band, static_cast<double*>(vel->p), vel->cstride, ctx->stream)
+                : launch_signed_normals<float>(phi->ndim, make_view<float>(phi), phi->h, min_norm, d_frozen, interface_band, static_cast<float*>(vel->p), vel->cstride, ctx->stream);
+        ctx->cnt.kernel_launches += 1;
+    }
+    if (e == cudaSuccess && rc == LSM_OK) {
+        double dx = phi->h[0];
+        for (int d = 1; d < phi->ndim; ++d) dx = std::min(dx, phi->h[d]);
+        const double tau = cfl * dx;
+        lsm_term term{};
+        term.kind = LSM_TERM_ADVECTION; term.scheme = LSM_UPWIND; term.coef_kind = LSM_COEF_FIELD; term.tscale_kind = LSM_TS_NONE; term.field = vel;
+        for (int it = 0; it < nb_iters && rc == LSM_OK; ++it) rc = stage_impl(ctx, LSM_FORWARD_EULER, 1, F, &term, 1, 0.0, tau, nullptr);
+    }
+    cudaStreamSynchronize(ctx->comm);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    if (d_frozen) cudaFree(d_frozen);
+    field_free(vel);
+    restore();
+    if (rc != LSM_OK) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(LSM_ERR_CUDA, "extend_along_normals failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    F->version++;
+    return LSM_OK;
+}
+
 int32_t lsm_max_abs_diff(lsm_ctx* ctx, const lsm_field* a, const lsm_field* b, double* out) {
     if (!ctx || !a || !b || !out) return fail(LSM_ERR_ARG, "null argument");
     if (a->ctx != ctx || b->ctx != ctx || a->dtype != b->dtype || a->ncomp != 1 || b->ncomp != 1 || a->owned != b->owned)

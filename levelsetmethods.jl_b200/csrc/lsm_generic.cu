@@ -576,6 +576,50 @@ cudaError_t launch_measure(int ndim, bool perimeter, const View<T>& v, const dou
 template cudaError_t launch_measure<float>(int, bool, const View<float>&, const double*, double*, int, double*, cudaStream_t);
 template cudaError_t launch_measure<double>(int, bool, const View<double>&, const double*, double*, int, double*, cudaStream_t);
 
+// velocityextension.jl:95-116 (_signed_normal_components) + :82-93 (frozen mask): a_d = S * grad_d / |grad|, S = phi/sqrt(phi^2+dx^2),
+// written SoA; zero where |grad|^2 <= min_norm^2 (reference) and on frozen nodes (so that the advection step leaves them untouched).
+template <int N, class T>
+__global__ void __launch_bounds__(256) signed_normals_kernel(const __grid_constant__ View<T> v, const double h0, const double h1, const double h2,
+                                                             const double dx, const double min2, const unsigned char* __restrict__ frozen,
+                                                             const double band_dx, T* __restrict__ a, const long cstride) {
+    const double h[3] = {h0, h1, h2};
+    const long total = (long)v.n[0] * v.n[1] * v.n[2];
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i0 = (int)(idx % v.n[0]);
+        const long q = idx / v.n[0];
+        const int i1 = (int)(q % v.n[1]), i2 = (int)(q / v.n[1]);
+        const T p = v.p[(long)i0 + (long)i1 * v.s1 + (long)i2 * v.s2];
+        const bool fr = frozen ? frozen[idx] != 0 : (fabs(double(p)) <= band_dx);
+        T g[3] = {T(0), T(0), T(0)};
+        T nrm2 = T(0);
+#pragma unroll
+        for (int d = 0; d < N; ++d) {
+            const T pp = getindex_slow<N, T>(v, i0 + (d == 0), i1 + (d == 1), i2 + (d == 2));
+            const T pm = getindex_slow<N, T>(v, i0 - (d == 0), i1 - (d == 1), i2 - (d == 2));
+            g[d] = T(double(T(pp - pm)) / (2 * h[d]));
+            nrm2 = d == 0 ? T(g[d] * g[d]) : T(nrm2 + T(g[d] * g[d]));
+        }
+        const bool zero = fr || double(nrm2) <= min2;
+        const T invn = T(1) / T(sqrt(nrm2));
+        const double S = double(p) / sqrt(double(T(p * p)) + dx * dx);
+#pragma unroll
+        for (int d = 0; d < N; ++d) a[(long)d * cstride + idx] = zero ? T(0) : T((S * double(g[d])) * double(invn));
+    }
+}
+template <class T>
+cudaError_t launch_signed_normals(int ndim, const View<T>& v, const double* h, double min_norm, const unsigned char* d_frozen, double band, T* a, long cstride, cudaStream_t s) {
+    double dx = h[0];
+    for (int d = 1; d < ndim; ++d) dx = h[d] < dx ? h[d] : dx;
+    const long total = (long)v.n[0] * v.n[1] * v.n[2];
+    long grid = (total + 255) / 256; if (grid > 148L * 16) grid = 148L * 16; if (grid < 1) grid = 1;
+    if (ndim == 1) signed_normals_kernel<1, T><<<(unsigned)grid, 256, 0, s>>>(v, h[0], h[1], h[2], dx, min_norm * min_norm, d_frozen, band * dx, a, cstride);
+    else if (ndim == 2) signed_normals_kernel<2, T><<<(unsigned)grid, 256, 0, s>>>(v, h[0], h[1], h[2], dx, min_norm * min_norm, d_frozen, band * dx, a, cstride);
+    else signed_normals_kernel<3, T><<<(unsigned)grid, 256, 0, s>>>(v, h[0], h[1], h[2], dx, min_norm * min_norm, d_frozen, band * dx, a, cstride);
+    return cudaGetLastError();
+}
+template cudaError_t launch_signed_normals<float>(int, const View<float>&, const double*, double, const unsigned char*, double, float*, long, cudaStream_t);
+template cudaError_t launch_signed_normals<double>(int, const View<double>&, const double*, double, const unsigned char*, double, double*, long, cudaStream_t);
+
 // K6: max |a - b| (bit-pattern max, NaN wins)
 template <class T>
 __global__ void __launch_bounds__(256) max_abs_diff_kernel(const T* __restrict__ a, const T* __restrict__ b, long n, unsigned long long* out) {

@@ -637,6 +637,54 @@ template <class F> double pairwise_sum(F&& f, long first, long last) {
     return v1 + v2;
 }
 
+// velocityextension.jl:20-69, 95-116
+template <int N, class T>
+void extend_impl(const orc_field& pf, T* Fv, int nb_iters, double cfl, const uint8_t* frozen, double band, double min_norm) {
+    orc_field d = pf;
+    bool any = false;
+    for (int k = 0; k < N; ++k) if (d.bc[k][0].kind != ORC_BC_NONE) any = true;
+    if (!any) for (int k = 0; k < N; ++k) { d.bc[k][0] = {ORC_BC_EXTRAP, 1}; d.bc[k][1] = {ORC_BC_EXTRAP, 1}; }
+    Field<N, T> phi(d);
+    long tot = 1; for (int k = 0; k < N; ++k) tot *= phi.n[k];
+    double dx = phi.h[0]; for (int k = 1; k < N; ++k) dx = std::min(dx, phi.h[k]);
+    const double tau = cfl * dx;
+    std::vector<uint8_t> mask(tot);
+    std::vector<T> comp[3];
+    for (int k = 0; k < N; ++k) comp[k].assign(tot, T(0));
+    const double mn2 = min_norm * min_norm;
+    const int n1 = phi.n[0], n2 = N > 1 ? phi.n[1] : 1, n3 = N > 2 ? phi.n[2] : 1;
+    long l = 0;
+    for (int k3 = 1; k3 <= n3; ++k3) for (int k2 = 1; k2 <= n2; ++k2) for (int k1 = 1; k1 <= n1; ++k1, ++l) {
+        Idx I{{k1, k2, k3}};
+        const T p = phi.raw(I);
+        mask[l] = frozen ? frozen[l] : (std::fabs(double(p)) <= band * dx);
+        T g[3]; T nrm2 = T(0);
+        for (int dd = 0; dd < N; ++dd) { g[dd] = T(D0(phi, I, dd)); nrm2 = dd == 0 ? T(g[dd] * g[dd]) : T(nrm2 + T(g[dd] * g[dd])); }
+        if (double(nrm2) <= mn2) continue;
+        const T invn = T(1) / T(std::sqrt(nrm2));
+        const double S = double(p) / std::sqrt(double(T(p * p)) + dx * dx);
+        for (int dd = 0; dd < N; ++dd) comp[dd][l] = T(S * double(g[dd]) * double(invn));
+    }
+    orc_field fd = d; fd.vals = Fv;
+    std::vector<T> Fnew(tot);
+    for (int it = 0; it < nb_iters; ++it) {
+        Field<N, T> Fw(fd);
+        l = 0;
+        for (int k3 = 1; k3 <= n3; ++k3) for (int k2 = 1; k2 <= n2; ++k2) for (int k1 = 1; k1 <= n1; ++k1, ++l) {
+            Idx I{{k1, k2, k3}};
+            if (mask[l]) { Fnew[l] = Fw.raw(I); continue; }
+            double adv = 0.0;      // zero(eltype(F_new)) + a*dF promotes to Float64 at the first += (dF is Float64)
+            for (int dd = 0; dd < N; ++dd) {
+                const T a = comp[dd][l];
+                const double dF = a > T(0) ? Dm(Fw, I, dd) : Dp(Fw, I, dd);
+                adv = adv + double(a) * dF;
+            }
+            Fnew[l] = T(double(Fw.raw(I)) - tau * adv);
+        }
+        std::memcpy(Fv, Fnew.data(), tot * sizeof(T));
+    }
+}
+
 #define DISPATCH(f, ...)                                                      \
     do {                                                                      \
         const int nd_ = (f)->ndim; const bool f32_ = (f)->dtype == ORC_F32;   \
@@ -788,6 +836,12 @@ void orc_eikonal_s0(const orc_field* phi0, double* out) {
             out[l++] = double(v) / std::sqrt(double(T(v * v)) + dx * dx);     // v / sqrt(v^2 + Δx^2)
         }
     });
+}
+
+int orc_extend_along_normals(const orc_field* phi, void* F, int nb_iters, double cfl, const uint8_t* frozen, double band, double min_norm) {
+    if (nb_iters < 0 || !(cfl > 0) || band < 0 || min_norm < 0) return 1;
+    DISPATCH(phi, { extend_impl<N, T>(*phi, (T*)F, nb_iters, cfl, frozen, band, min_norm); });
+    return 0;
 }
 
 int orc_nstages(int integ) { return nstages(integ); }

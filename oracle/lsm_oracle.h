@@ -118,6 +118,11 @@ int    orc_integrate(const orc_field* desc, int integrator, double cfl, void* ph
                      const orc_term* terms, int nterms, double t0, double tf, double dt_max,
                      int64_t max_steps, double* t_out, int64_t* steps_out);
 
+/* velocityextension.jl:20-116 : extend_along_normals!(F, phi; nb_iters, cfl, frozen, interface_band, min_norm).
+ * F: array of phi's dtype and owned shape; frozen: nullable uint8 mask (1 = frozen). */
+int    orc_extend_along_normals(const orc_field* phi, void* F, int nb_iters, double cfl, const uint8_t* frozen,
+                                double interface_band, double min_norm);
+
 #ifdef __cplusplus
 }
 #endif

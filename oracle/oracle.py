@@ -90,6 +90,7 @@ def lib():
         L.orc_stage.argtypes = [fp, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, tp, C.c_int, dbl, dbl,
                                 C.POINTER(dbl)]
         L.orc_stage.restype = C.c_int
+        L.orc_extend_along_normals.argtypes = [fp, C.c_void_p, C.c_int, dbl, C.c_void_p, dbl, dbl]; L.orc_extend_along_normals.restype = C.c_int
         L.orc_nstages.argtypes = [C.c_int]; L.orc_nstages.restype = C.c_int
         L.orc_advance.argtypes = [fp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, tp, C.c_int, dbl, dbl]
         L.orc_advance.restype = C.c_int
@@ -345,3 +346,16 @@ def integrate(phi: Field, integrator, terms, tf, t0=0.0, cfl=0.5, dt_max=float("
     if rc == 2:
         raise ValueError(f"final time {tf} must be >= initial time {t0}")
     return t_out.value, steps.value
+
+
+def extend_along_normals(F: np.ndarray, phi: Field, nb_iters=50, cfl=0.45, frozen=None, interface_band=1.5, min_norm=1e-14):
+    """``extend_along_normals!`` (velocityextension.jl:20-69).  Mutates and returns ``F`` (same dtype/shape as phi, F-order)."""
+    assert F.flags.f_contiguous and F.dtype == phi.vals.dtype and F.shape == phi.vals.shape
+    fr = None
+    if frozen is not None:
+        fr = np.asfortranarray(frozen.astype(np.uint8))
+    rc = lib().orc_extend_along_normals(C.byref(phi.c()), F.ctypes.data, int(nb_iters), float(cfl),
+                                        None if fr is None else fr.ctypes.data, float(interface_band), float(min_norm))
+    if rc:
+        raise ValueError("invalid extend_along_normals arguments")
+    return F

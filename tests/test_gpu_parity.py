@@ -431,6 +431,36 @@ def test_eikonal_reinitialize_prehook(m, O):
     assert np.isfinite(eq.state.peek()).all()
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_extend_along_normals(m, O, strict, dtype):
+    """extend_along_normals! on the device against the oracle's restatement of velocityextension.jl:20-116,
+    2-D (the grid of test-velocityextension.jl) and 3-D, default band mask and an explicit Bool mask, strict and tiled kernels."""
+    ctx = m.default_context()
+    for n, lc, hc in (((81, 61), (-1, -1), (1, 1)), ((30, 28, 26), (-1, -1, -1), (1, 1, 1))):
+        X = H.coords(lc, hc, n)
+        r = np.sqrt(sum(x * x for x in X))
+        phi0 = H.bcast((r - 0.5) * (1 + 0.2 * X[0]), n).astype(dtype)
+        F0 = H.bcast(np.sin(3 * X[0]) + X[1] ** 2, n).astype(dtype)
+        mask = np.asfortranarray(np.abs(phi0) < 0.08)
+        for frozen in (None, mask):
+            for bc in (None, "neumann"):
+                fo = O.Field(phi0.copy(order="F"), lc, hc, bc=None if bc is None else O.NEUMANN)
+                Fo = O.extend_along_normals(F0.copy(order="F"), fo, nb_iters=12, frozen=frozen)
+                for kernel in (1, 0):
+                    ctx.set_option(OPT_KERNEL, kernel)
+                    g = m.CartesianGrid(lc, hc, n)
+                    phi = m.MeshField(phi0.copy(order="F"), g, bc=None if bc is None else m.NeumannBC())
+                    F = m.MeshField(F0.copy(order="F"), g)
+                    m.extend_along_normals(F, phi, nb_iters=12, frozen=frozen)
+                    d = np.abs(F.peek().astype(np.float64) - Fo.astype(np.float64)).max()
+                    tol = (1e-13 if kernel == 1 else 1e-11) if dtype == np.float64 else 2e-5
+                    assert d <= tol, (n, frozen is not None, bc, kernel, d)
+                    if frozen is not None:
+                        assert np.array_equal(F.peek()[mask], F0[mask])          # Dirichlet constraint on frozen nodes
+    with pytest.raises(ValueError):
+        m.extend_along_normals(F, phi, nb_iters=-1)
+
+
 def test_counters_and_launch_accounting(m):
     ctx = m.default_context()
     case = H.c3_enright(32)
