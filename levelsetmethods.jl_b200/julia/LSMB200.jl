@@ -222,4 +222,39 @@ function integrate!(eq::LSM.LevelSetEquation, tf, Δt = Inf; prehook = identity,
     return eq
 end
 
+"""
+    volume(ϕ::MeshField; ctx) / perimeter(ϕ::MeshField; ctx)
+
+Device reductions for `LevelSetMethods.volume` / `perimeter` (src/levelsetops.jl:27-33,139-149).
+"""
+function volume(ϕ::LSM.MeshField; ctx::Context = default_context())
+    d = DeviceField(ctx, ϕ); out = Ref{Float64}(0)
+    check(ccall((:lsm_volume, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Float64}), ctx.handle, d.handle, out))
+    return out[]
+end
+function perimeter(ϕ::LSM.MeshField; ctx::Context = default_context())
+    d = DeviceField(ctx, ϕ); out = Ref{Float64}(0)
+    check(ccall((:lsm_perimeter, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Float64}), ctx.handle, d.handle, out))
+    return out[]
+end
+
+"""
+    extend_along_normals!(F, ϕ; nb_iters = 50, cfl = 0.45, frozen = nothing, interface_band = 1.5, min_norm = 1.0e-14, ctx)
+
+Drop-in for `LevelSetMethods.extend_along_normals!` (src/velocityextension.jl:20-78) on dense fields.
+"""
+function extend_along_normals!(F::LSM.MeshField, ϕ::LSM.MeshField; nb_iters::Integer = 50, cfl::Real = 0.45, frozen = nothing,
+                               interface_band::Real = 1.5, min_norm::Real = 1.0e-14, ctx::Context = default_context())
+    size(values(F)) == size(values(ϕ)) || throw(ArgumentError("F must have the same size as ϕ"))
+    frozen === nothing || size(frozen) == size(values(ϕ)) || throw(ArgumentError("frozen mask must have the same size as ϕ"))
+    dF, dϕ = DeviceField(ctx, F), DeviceField(ctx, ϕ)
+    mask = frozen === nothing ? UInt8[] : UInt8.(frozen)
+    GC.@preserve mask check(ccall((:lsm_extend_along_normals, LIB), Int32,
+                                  (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Float64, Ptr{UInt8}, Float64, Float64),
+                                  ctx.handle, dF.handle, dϕ.handle, nb_iters, cfl, frozen === nothing ? C_NULL : pointer(mask),
+                                  interface_band, min_norm))
+    download!(dF)
+    return F
+end
+
 end # module

@@ -273,3 +273,46 @@ def test_stage_api_equals_advance(O):
         for s in range(1, O.nstages(integ) + 1):
             O.stage(g, integ, s, b1, b2, terms, 0.0, 1e-3)
         assert np.array_equal(f.vals, g.vals)
+
+
+# ---- test/test-velocityextension.jl:19-44 "Extend Along Normals" and :46-87 "Circle periodic extension" ----
+def test_extend_along_normals_reference_tests(O):
+    f = mk(O, lambda x, y: x + 0 * y, (-1.0, -1.0), (1.0, 1.0), (81, 61))
+    X = f.nodes()
+    d = min(f.meshsize(1), f.meshsize(2))
+    frozen = np.asfortranarray(np.abs(f.vals) <= d)
+    Fref = np.broadcast_to(np.sin(np.pi * X[1]), f.vals.shape)
+    F = np.asfortranarray(np.where(frozen, Fref, 0.0))
+    seed = F.copy()
+    out = O.extend_along_normals(F, f, nb_iters=150, frozen=frozen, cfl=0.45)
+    assert np.abs(out - Fref).max() < 0.08
+    assert np.array_equal(out[frozen], seed[frozen])
+
+    R = 0.55
+    f = mk(O, lambda x, y: np.sqrt(x * x + y * y) - R, (-1.0, -1.0), (1.0, 1.0), (121, 121), bc=O.PERIODIC)
+    X = f.nodes()
+    d = f.meshsize(1)
+    r = np.sqrt(X[0] ** 2 + X[1] ** 2)
+    frozen = np.asfortranarray(np.abs(f.vals) <= 1.1 * d)
+    v = np.asfortranarray(np.where(frozen, np.broadcast_to(X[1], r.shape) / np.maximum(r, np.finfo(float).eps), 0.0))
+    seed = v.copy()
+    out = O.extend_along_normals(v, f, nb_iters=100, frozen=frozen, cfl=0.45)
+    assert np.array_equal(out[frozen], seed[frozen])
+    vf = O.Field(out, (-1.0, -1.0), (1.0, 1.0), bc=O.PERIODIC)
+    tot, cnt = 0.0, 0
+    for i in range(1, 121):            # active_nodeindices of a periodic field: node n duplicates node 1
+        for j in range(1, 121):
+            if abs(f.vals[i - 1, j - 1]) <= 5.0 * d and not frozen[i - 1, j - 1]:
+                gx, gy = f.deriv("D0", (i, j), 1), f.deriv("D0", (i, j), 2)
+                nn = math.hypot(gx, gy)
+                if nn == 0 or math.isnan(nn):
+                    continue
+                tot += abs(gx / nn * vf.deriv("D0", (i, j), 1) + gy / nn * vf.deriv("D0", (i, j), 2))
+                cnt += 1
+    assert cnt > 100 and tot / cnt < 0.12
+    # default mask = |phi| <= interface_band * dx; nb_iters = 0 leaves F untouched
+    F0 = np.asfortranarray(np.random.default_rng(0).standard_normal(f.vals.shape))
+    assert np.array_equal(O.extend_along_normals(F0.copy(order="F"), f, nb_iters=0), F0)
+    out = O.extend_along_normals(F0.copy(order="F"), f, nb_iters=3)
+    band = np.abs(f.vals) <= 1.5 * d
+    assert np.array_equal(out[band], F0[band]) and not np.array_equal(out[~band], F0[~band])
