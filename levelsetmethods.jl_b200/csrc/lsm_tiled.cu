@@ -27,6 +27,7 @@
 //
 // Compiled with FMA contraction ON.  Parity with the CPU oracle is checked in tests/ (<= 1e-10 after
 // 100 RK3 steps in Float64, <= 1e-4 in Float32).
+#include <type_traits>
 #include <cstdint>
 #include <cstdlib>
 #include <cuda.h>          // CUtensorMap + enums only; cuTensorMapEncodeTiled is looked up at run time (no libcuda link)
@@ -40,6 +41,9 @@ namespace {
 
 #ifndef LSM_MINB_2D
 #define LSM_MINB_2D 4      // 2-D blocks process a single tile (load, wait, compute): latency bound, so favour resident blocks
+#endif
+#ifndef LSM_MINB_EIK
+#define LSM_MINB_EIK 3    // Eikonal kernel: latency-bound at 16 warps/SM (ncu: 'wait' + short-scoreboard stalls lead); 3 blocks of 74 KB fit
 #endif
 constexpr int HAL = 3;           // WENO5 reach; every term's stencil fits in it
 
@@ -174,10 +178,38 @@ __device__ __forceinline__ double weno5_up<float>(float q0, float q1, float q2, 
     return double(fmaf(num, __frcp_rn(den), d2));
 }
 
+// x / 3 correctly rounded without the generic division sequence (timestepping.jl:194 divides by 3 in the storage type):
+// q0 = RN(x * RN(1/3)), r = x - 3 q0 (exact in an FMA), q = RN(q0 + r * RN(1/3)) is the correctly rounded quotient when the
+// reciprocal is correctly rounded and q0 is within one ulp (Markstein's theorem; 3 has no all-ones significand).
+__device__ __forceinline__ double div3(double x) {
+    const double q = x * (1.0 / 3.0);
+    return fma(fma(-3.0, q, x), 1.0 / 3.0, q);
+}
+__device__ __forceinline__ float div3(float x) {
+    const float q = x * (1.0f / 3.0f);
+    return fmaf(fmaf(-3.0f, q, x), 1.0f / 3.0f, q);
+}
+
+// Static term signature of the multi-term instantiations: TK packs the kind of term k in bits [3k, 3k+3)
+// (SK_* below; TK < 0: kinds are runtime data), COEFK packs its coefficient kind in bits [2k, 2k+2) (COEFK < 0: runtime).
+enum : int { SK_ADV_WENO = 0, SK_ADV_UPWIND = 1, SK_NORMAL = 2, SK_CURV = 3, SK_EIK = 4 };
+__host__ __device__ constexpr int sig_kind(int TK, int k) { return TK < 0 || k < 0 ? -1 : ((TK >> (3 * k)) & 7); }
+__host__ __device__ constexpr int sig_coef(int COEFK, int k) { return COEFK < 0 || k < 0 ? -1 : ((COEFK >> (2 * k)) & 3); }
+// first staged aux tile of term k when every FIELD coefficient before it is staged (the launcher checks)
+__host__ __device__ constexpr int sig_first(int TK, int COEFK, int k, int ndim) {
+    int f = 0;
+    for (int j = 0; j < k; ++j)
+        if (sig_coef(COEFK, j) == COEF_FIELD) f += (sig_kind(TK, j) == SK_ADV_WENO || sig_kind(TK, j) == SK_ADV_UPWIND) ? ndim : 1;
+    return f;
+}
+
 // levelsetterms.jl:184-187
+// Same-sign test on the sign bits (LOP3 + ISETP instead of DMUL + DSETP): identical to `x*y > 0` except where the product
+// underflows (|x||y| < 5e-324), where the reference returns 0 and this returns min(|x|,|y|) < 1e-150 — far below any tolerance.
+// x == 0 or y == 0 selects the zero operand, as the reference's 0 result.
 __device__ __forceinline__ double minmod(double x, double y) {
-    if (!(x * y > 0.0)) return 0.0;
-    return fabs(x) <= fabs(y) ? x : y;
+    const double m = fabs(x) <= fabs(y) ? x : y;
+    return (__double2hiint(x) ^ __double2hiint(y)) < 0 ? 0.0 : m;
 }
 
 template <class T, int NDIM, int TX, int TY, int NY>
@@ -229,8 +261,8 @@ __device__ __forceinline__ int remap_index(int i, int n, int kind_lo, int kind_h
 // Fused stage kernel.  MASK = which term kinds the instantiation carries code for; the terms themselves
 // (order, coefficients) are runtime data, applied one after the other like the reference
 // (x = base; x -= c*H_1; x -= c*H_2; ..., timestepping.jl:128-202).
-template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL, int TX, int TY, int NY, int MINB>
-__global__ void __launch_bounds__(TX * TY, (NDIM == 2 ? LSM_MINB_2D : MINB))
+template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL, int TX, int TY, int NY, int MINB, int TK>
+__global__ void __launch_bounds__(TX * TY, (NDIM == 2 ? LSM_MINB_2D : (MASK == M_EIK && TK >= 0 ? LSM_MINB_EIK : MINB)))
 stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ AuxList A, const __grid_constant__ TmaMaps M, const int cz) {
     using G = TileGeom<T, NDIM, TX, TY, NY>;
     constexpr int RING = G::RING;
@@ -366,7 +398,7 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
     // separable velocity u_d = ((s_d X_d[i]) Y_d[j]) Z_d[z] (single-term advection kernels): the x-y factor is a per-thread
     // loop invariant, the z factor is block-uniform — same product order as the reference-side tables, so bit-identical
     double pxy[NY][3];
-    if (COEFK == COEF_SEPARABLE) {
+    if (TK < 0 && COEFK == COEF_SEPARABLE) {
 #pragma unroll
         for (int k = 0; k < NY; ++k) {
             const int jj = min(y0 + ty + k * TY, n1 - 1), ii = min(i, n0 - 1);
@@ -387,6 +419,14 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
 #pragma unroll
     for (int k = 0; k < NY; ++k) lin_k[k] = (long)i + (long)(y0 + ty + k * TY) * vs1 + (long)zbeg * vs2;
 
+    // which of this thread's NY nodes exist (partial tiles / 2-D row range): a loop invariant kept as a bit mask
+    unsigned act = 0;
+#pragma unroll
+    for (int k = 0; k < NY; ++k) {
+        const int j = y0 + ty + k * TY;
+        if (i < n0 && j < n1 && (NDIM == 3 || (j >= ylo && j < yhi))) act |= 1u << k;
+    }
+
     for (int z = zbeg; z < zend; ++z) {
         unsigned txb = 0;
         if (NDIM == 3) {
@@ -403,7 +443,7 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
         for (int k = 0; k < NY; ++k) {
             const int r = ty + k * TY;
             const int j = y0 + r;
-            if (i < n0 && j < n1 && (NDIM == 3 || (j >= ylo && j < yhi))) {
+            if ((act >> k) & 1u) {
                 const int sc = (r + HAL) * G::W + tx + G::XL;
                 const int st = r * TX + tx;
                 const T* c0 = cur + sc;
@@ -426,16 +466,19 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                     return c0[off];
                 };
                 // coefficient component d of term k (times g(t))
-                auto coef_gen = [&](const TermDev& tm, int kk, int d, const bool SCALE) -> double {
+                auto coef_gen = [&](const TermDev& tm, int kk, int d, const bool SCALE, auto kc) -> double {
                     double v;
-                    const int ck = COEFK >= 0 ? COEFK : tm.coef_kind;      // compile-time for the single-term advection kernels
+                    constexpr int KK = decltype(kc)::value;                 // term index when it is a compile-time constant, else -1
+                    constexpr int SCK = sig_coef(COEFK, KK);                // compile-time coefficient kind (static signature)
+                    constexpr int SFIRST = TK >= 0 ? sig_first(TK, COEFK, KK, NDIM) : 0;
+                    const int ck = SCK >= 0 ? SCK : tm.coef_kind;
                     if (ck == COEF_FIELD) {
-                        if (COEFK >= 0 || A.first[kk] >= 0) v = double(auxz[((COEFK >= 0 ? 0 : A.first[kk]) + d) * G::TILE + st]);
+                        if (SCK >= 0 || A.first[kk] >= 0) v = double(auxz[((SCK >= 0 ? SFIRST : A.first[kk]) + d) * G::TILE + st]);
                         else {   // Float64 coefficient with a Float32 state (S0): read directly
                             const long node = (long)i + (long)j * vs1 + (long)z * vs2;
                             v = static_cast<const double*>(tm.coef)[(long)d * tm.cstride + node];
                         }
-                    } else if (COEFK == COEF_SEPARABLE) {
+                    } else if (TK < 0 && COEFK == COEF_SEPARABLE) {
                         v = pxy[k][d];
                         if (NDIM == 3) v = v * __ldg(tm.tab[d][2] + z);
                     } else if (ck == COEF_SEPARABLE) {
@@ -445,8 +488,8 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                     if (SCALE && tm.scaled) v = v * tm.g;
                     return v;
                 };
-                auto coef = [&](const TermDev& tm, int kk, int d) -> double { return coef_gen(tm, kk, d, true); };
-                auto coef_raw = [&](const TermDev& tm, int kk, int d) -> double { return coef_gen(tm, kk, d, false); };
+                auto coef = [&](const TermDev& tm, int kk, int d, auto kc) -> double { return coef_gen(tm, kk, d, true, kc); };
+                auto coef_raw = [&](const TermDev& tm, int kk, int d, auto kc) -> double { return coef_gen(tm, kk, d, false, kc); };
                 // second-order ENO pair along d, undivided: returns h*neg, h*pos (levelsetterms.jl:156-170, 252-265)
                 auto eno2 = [&](int d, double& ng, double& ps) {
                     const T pm2 = at(d, -2), pm1 = at(d, -1), pp1 = at(d, 1), pp2 = at(d, 2);
@@ -461,24 +504,35 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                 if (A.p0 >= 0) {
                     const T pn = auxz[A.p0 * G::TILE + st];
                     if (P.base == BASE_RK3_S2) x = T(fma(0.75, double(pn), 0.25 * double(qc)));       // timestepping.jl:183
-                    else if (P.base == BASE_RK3_S3) x = T((pn + T(2) * qc) / T(3));                   // timestepping.jl:194
+                    else if (P.base == BASE_RK3_S3) x = div3(T(pn + T(2) * qc));                       // timestepping.jl:194
                     else x = pn;                                                                       // RK2 S2 (corr)
                 }
                 T x2 = qc;
 
                 constexpr bool ONE = (MASK & (MASK - 1)) == 0;      // single kind: no runtime kind tests
-                auto one_term = [&](const TermDev& tm, const int kk) {
+                auto one_term = [&](const TermDev& tm, const int kk, auto kc) {
+                    constexpr int SKIND = sig_kind(TK, decltype(kc)::value);     // compile-time kind of this term (static signature) or -1
+                    constexpr int SCK = sig_coef(COEFK, decltype(kc)::value);
+                    const bool k_weno = SKIND >= 0 ? SKIND == SK_ADV_WENO : (ONE || (tm.kind == TERM_ADVECTION && tm.scheme == SCHEME_WENO5));
+                    const bool k_upw = SKIND >= 0 ? SKIND == SK_ADV_UPWIND : (ONE || tm.kind == TERM_ADVECTION);
+                    const bool k_god = SKIND >= 0 ? (SKIND == SK_NORMAL || SKIND == SK_EIK) : (ONE || tm.kind == TERM_NORMAL || tm.kind == TERM_EIKONAL);
+                    const bool k_curv = SKIND >= 0 ? SKIND == SK_CURV : (ONE || tm.kind == TERM_CURVATURE);
+                    const bool k_normal = SKIND >= 0 ? SKIND == SK_NORMAL : (MASK & M_NORMAL) && (!(MASK & M_EIK) || tm.kind == TERM_NORMAL);
+                    const bool c_none = SCK >= 0 ? SCK == COEF_NONE : tm.coef_kind == COEF_NONE;
                     double H = 0.0;
-                    if ((MASK & M_ADV_WENO) && (ONE || (tm.kind == TERM_ADVECTION && tm.scheme == SCHEME_WENO5))) {
+                    if ((MASK & M_ADV_WENO) && k_weno) {
                         // levelsetterms.jl:73-82 : H = sum_d u_d * weno(d) = sum_d (|u_d| / h_d) * W_d, left to right
                         const double g = tm.scaled ? tm.g : 1.0;
+                        const int ghi = __double2hiint(g);
                         double uu[3] = {0, 0, 0}, sest = 0.0;
 #pragma unroll
                         for (int d = 0; d < NDIM; ++d) {
-                            const double u = coef_raw(tm, kk, d);                 // velocity before the time factor g(t)
+                            const double u = coef_raw(tm, kk, d, kc);             // velocity before the time factor g(t)
                             if (do_cfl) { uu[d] = u; sest = fma(fabs(u), fabs(P.cfl_g) * ih[d], sest); }
                             // v = u*g; v > 0 selects the minus-biased stencil.  sign(v) = sign(u)*sign(g); |v|/h = |u| * (|g|/h)
-                            const int s = ((u > 0) & (g > 0)) | ((u < 0) & (g < 0)) ? 1 : -1;   // upwind-ordered sampling: q_k = phi[i - s*(3-k)]
+                            // s from the sign bits (integer ops instead of 8 DSETP): when u*g == 0 the reference takes the plus-biased
+                            // stencil but multiplies it by zero, so either ordering yields the same 0 contribution (a == 0).
+                            const int s = ((__double2hiint(u) ^ ghi) >> 31) | 1;                 // = sign(u*g); upwind-ordered sampling: q_k = phi[i - s*(3-k)]
                             const double w = weno5_up<T>(up(d, -3, s), up(d, -2, s), up(d, -1, s), qc, up(d, 1, s), up(d, 2, s));
                             const double a = fabs(u) * (fabs(g) * ih[d]);
                             H = d == 0 ? a * w : fma(a, w, H);
@@ -494,23 +548,23 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                             const unsigned long long bits = isnan(sx) ? 0x7FF8000000000000ULL : (unsigned long long)__double_as_longlong(sx);
                             cfl_best = bits > cfl_best ? bits : cfl_best;
                         }
-                    } else if ((MASK & M_ADV_UPWIND) && (ONE || tm.kind == TERM_ADVECTION)) {
+                    } else if ((MASK & M_ADV_UPWIND) && k_upw) {
 #pragma unroll
                         for (int d = 0; d < NDIM; ++d) {
-                            const double u = coef(tm, kk, d);
+                            const double u = coef(tm, kk, d, kc);
                             const double der = u > 0 ? double(T(qc - at(d, -1))) : double(T(at(d, 1) - qc));
                             const double a = u * ih[d];
                             H = d == 0 ? a * der : fma(a, der, H);
                         }
-                    } else if ((MASK & (M_NORMAL | M_EIK)) && (ONE || tm.kind == TERM_NORMAL || tm.kind == TERM_EIKONAL)) {
+                    } else if ((MASK & (M_NORMAL | M_EIK)) && k_god) {
                         // Godunov |grad phi| from the ENO2 pair (levelsetterms.jl:156-170, 252-265).  Only ONE of the two
                         // upwind selections is ever used at a node — grad+ when the sign source (speed v, frozen S0, or phi
                         // itself) is > 0, grad- otherwise — so only that one is accumulated.
                         double cf = 0.0;                      // v or S0
                         bool sp;
-                        if (tm.kind == TERM_NORMAL) { cf = coef(tm, kk, 0); sp = cf > 0; }
-                        else if (tm.coef_kind == COEF_NONE) sp = qc > T(0);
-                        else { cf = coef(tm, kk, 0); sp = cf > 0; }
+                        if (k_normal) { cf = coef(tm, kk, 0, kc); sp = cf > 0; }
+                        else if (c_none) sp = qc > T(0);
+                        else { cf = coef(tm, kk, 0, kc); sp = cf > 0; }
                         double gsel = 0.0;
 #pragma unroll
                         for (int d = 0; d < NDIM; ++d) {
@@ -522,18 +576,18 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                             gsel = fma(fma(a, a, b * b), ih[d] * ih[d], gsel);
                         }
                         const double nrm = sqrt(gsel);
-                        if (tm.kind == TERM_NORMAL) {
+                        if (k_normal) {
                             // positive(v)*sqrt(grad+) + negative(v)*sqrt(grad-): one of the two products is exactly 0
                             // (a NaN speed gives 0 like positive()/negative() do)
                             H = (cf > 0 ? cf : (cf < 0 ? cf : 0.0)) * nrm;
-                        } else if (tm.coef_kind == COEF_NONE) {          // live sign, O&F 7.6 (levelsetterms.jl:237-242)
+                        } else if (c_none) {                             // live sign, O&F 7.6 (levelsetterms.jl:237-242)
                             const double den = sqrt(double(T(qc * qc)) + (nrm * nrm) * (P.dxmin * P.dxmin));
                             const double S = den == 0.0 ? 0.0 : double(qc) / den;
                             H = S * (nrm - 1.0);
                         } else {                                         // frozen sign, O&F 7.5 (levelsetterms.jl:243-247)
                             H = cf * (nrm - 1.0);
                         }
-                    } else if ((MASK & M_CURV) && (ONE || tm.kind == TERM_CURVATURE)) {
+                    } else if ((MASK & M_CURV) && k_curv) {
                         // levelsetterms.jl:111-121 + levelsetops.jl:197-244:  b * kappa * |grad phi| = b * (tr(H) q - g'Hg) / q
                         double g[3] = {0, 0, 0}, Hd[3] = {0, 0, 0};
 #pragma unroll
@@ -558,17 +612,18 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                             quad = fma(Hd[2] * g[2], g[2], quad) + 2.0 * (h02 * g[0] * g[2] + h12 * g[1] * g[2]);
                         }
                         const double eps = sizeof(T) == 8 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
-                        const double b = coef(tm, kk, 0);
+                        const double b = coef(tm, kk, 0, kc);
                         H = q < eps ? b * 0.0 : b * (fma(tr, q, -quad) * fast_rcp<2>(q));
                     }
                     x = T(fma(-P.c, H, double(x)));
                     if (P.out2) x2 = T(fma(-P.c2, H, double(x2)));
                 };
                 if (NTS > 0) {
-#pragma unroll
-                    for (int kk = 0; kk < NTS; ++kk) one_term(P.terms[kk], kk);
+                    one_term(P.terms[0], 0, std::integral_constant<int, 0>{});
+                    if (NTS > 1) one_term(P.terms[1], 1, std::integral_constant<int, 1>{});
+                    static_assert(NTS <= 2, "static term lists hold at most two terms");
                 } else {
-                    for (int kk = 0; kk < P.nterms; ++kk) one_term(P.terms[kk], kk);
+                    for (int kk = 0; kk < P.nterms; ++kk) one_term(P.terms[kk], kk, std::integral_constant<int, -1>{});
                 }
                 const long lin = lin_k[k];
                 P.out[lin] = x;
@@ -638,11 +693,11 @@ bool encode_map3(CUtensorMap* m, const void* base, long n0, long n1, long nplane
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL = false>
+template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL = false, int TK = -1>
 cudaError_t launch_tiled(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
     constexpr int TX = LSM_TX, TY = LSM_TY, NY = LSM_NY;
     using G = TileGeom<T, NDIM, TX, TY, NY>;
-    auto kern = stage_tiled_kernel<T, NDIM, MASK, NTS, COEFK, REMAP, FCFL, TX, TY, NY, LSM_MINB>;
+    auto kern = stage_tiled_kernel<T, NDIM, MASK, NTS, COEFK, REMAP, FCFL, TX, TY, NY, LSM_MINB, TK>;
     const size_t smem = G::smem_bytes(A.n);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
@@ -692,9 +747,32 @@ cudaError_t launch_by_mask(int mask, const StageParams<T>& P, const AuxList& A, 
                     if (t0.coef_kind == COEF_CONST) return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_CONST, REMAP>(P, A, s);
                 }
                 break;
-            case M_EIK:                 if (P.nterms == 1) return launch_tiled<T, NDIM, M_EIK, 1, -1, REMAP>(P, A, s); break;
-            case M_NORMAL | M_ADV_WENO: if (P.nterms == 2) return launch_tiled<T, NDIM, M_NORMAL | M_ADV_WENO, 2, -1, REMAP>(P, A, s); break;
-            case M_ADV_WENO | M_CURV:   if (P.nterms == 2) return launch_tiled<T, NDIM, M_ADV_WENO | M_CURV, 2, -1, REMAP>(P, A, s); break;
+            // static signatures (term kinds, coefficient kinds and aux-tile slots known at compile time) for the BASELINE
+            // configurations; any other ordering / coefficient kind takes the runtime-dispatch instantiation of the same mask
+            case M_EIK:
+                if (P.nterms == 1) {
+                    const TermDev& t0 = P.terms[0];
+                    if (t0.coef_kind == COEF_FIELD && A.first[0] == 0) return launch_tiled<T, NDIM, M_EIK, 1, COEF_FIELD, REMAP, false, SK_EIK>(P, A, s);
+                    if (t0.coef_kind == COEF_NONE) return launch_tiled<T, NDIM, M_EIK, 1, COEF_NONE, REMAP, false, SK_EIK>(P, A, s);
+                    return launch_tiled<T, NDIM, M_EIK, 1, -1, REMAP>(P, A, s);
+                }
+                break;
+            case M_NORMAL | M_ADV_WENO:
+                if (P.nterms == 2) {
+                    const TermDev &t0 = P.terms[0], &t1 = P.terms[1];
+                    if (t0.kind == TERM_NORMAL && t0.coef_kind == COEF_FIELD && A.first[0] == 0 && t1.coef_kind == COEF_FIELD && A.first[1] == 1)
+                        return launch_tiled<T, NDIM, M_NORMAL | M_ADV_WENO, 2, COEF_FIELD | (COEF_FIELD << 2), REMAP, false, SK_NORMAL | (SK_ADV_WENO << 3)>(P, A, s);
+                    return launch_tiled<T, NDIM, M_NORMAL | M_ADV_WENO, 2, -1, REMAP>(P, A, s);
+                }
+                break;
+            case M_ADV_WENO | M_CURV:
+                if (P.nterms == 2) {
+                    const TermDev &t0 = P.terms[0], &t1 = P.terms[1];
+                    if (t0.kind == TERM_ADVECTION && t0.coef_kind == COEF_FIELD && A.first[0] == 0 && t1.coef_kind == COEF_CONST)
+                        return launch_tiled<T, NDIM, M_ADV_WENO | M_CURV, 2, COEF_FIELD | (COEF_CONST << 2), REMAP, false, SK_ADV_WENO | (SK_CURV << 3)>(P, A, s);
+                    return launch_tiled<T, NDIM, M_ADV_WENO | M_CURV, 2, -1, REMAP>(P, A, s);
+                }
+                break;
             default: break;
         }
     }

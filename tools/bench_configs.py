@@ -46,7 +46,7 @@ def run(name, case, integ, balg, steps, warmup=3):
                                   C.byref(t_out), C.byref(n)))
         return t_out.value
 
-    t = go(warmup, 0.0)
+    t = go(warmup, 0.0) if warmup > 0 else 0.0
     ctx.set_option(L.OPT_TIME_STAGES, 1)
     ctx.sync(); ctx.reset_counters()
     ctx.event_record(0)
@@ -72,6 +72,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--only", default="")
+    ap.add_argument("--skip", default="")
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--kernel", type=int, default=0)
     a = ap.parse_args()
     m.default_context().set_option(L.OPT_KERNEL, a.kernel)
@@ -88,9 +90,9 @@ def main():
         ("C5 3-D normal motion + advection 512^3 f64 (1-GPU slice of the 1024^3 config)", lambda: H.c5_normal_advection(512, f64), m.RK3(), 160.0),
     ]
     for name, mk, integ, balg in cfgs:
-        if a.only and not name.startswith(a.only):
+        if (a.only and not name.startswith(a.only)) or (a.skip and name.startswith(a.skip)):
             continue
-        run(name, mk(), integ, balg, a.steps if "128^2" not in name else 200)
+        run(name, mk(), integ, balg, a.steps if "128^2" not in name else 10 * a.steps, a.warmup)
 
 
 if __name__ == "__main__":
