@@ -208,6 +208,13 @@ int32_t lsm_perimeter(lsm_ctx* ctx, lsm_field* phi, double* out);
 int32_t lsm_extend_along_normals(lsm_ctx* ctx, lsm_field* F, lsm_field* phi, int32_t nb_iters, double cfl, const uint8_t* frozen,
                                  double interface_band, double min_norm);
 
+/* Set operations on level sets, in place on the device (levelsetops.jl:253-325, "next" row 3):
+ *   LSM_CSG_UNION      dst = min(dst, src)   union!      LSM_CSG_INTERSECT  dst = max(dst, src)   intersect!
+ *   LSM_CSG_SETDIFF    dst = max(dst, -src)  setdiff!    LSM_CSG_COMPLEMENT dst = -dst (src NULL) complement!
+ * min/max follow Julia: NaN if either operand is NaN, min(0.0,-0.0) = -0.0, max(0.0,-0.0) = 0.0. */
+enum { LSM_CSG_UNION = 0, LSM_CSG_INTERSECT = 1, LSM_CSG_SETDIFF = 2, LSM_CSG_COMPLEMENT = 3 };
+int32_t lsm_field_csg(lsm_ctx* ctx, lsm_field* dst, const lsm_field* src, int32_t op);
+
 /* ---- diagnostics (test harness) -------------------------------------------- */
 /* max |a - b| over all owned nodes, all-reduced over ranks. */
 int32_t lsm_max_abs_diff(lsm_ctx* ctx, const lsm_field* a, const lsm_field* b, double* out);

@@ -12,6 +12,7 @@ from .api import (Context, default_context, set_default_context, CartesianGrid, 
                   TimeScaled, SeparableVelocity, LevelSetTerm, AdvectionTerm, CurvatureTerm, NormalMotionTerm,
                   EikonalReinitializationTerm, update_term, compute_cfl, TimeIntegrator, ForwardEuler, RK2, RK3,
                   LevelSetEquation, current_state, current_time, integrate, integrate_bang, volume, perimeter, eikonal_reinitialize, extend_along_normals,
+    union, union_, intersect, intersect_, setdiff, setdiff_, complement, complement_,
                   _normalize_bc, _add_boundary_conditions)
 
 __all__ = [n for n in dir() if not n.startswith("__")]

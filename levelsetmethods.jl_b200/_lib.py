@@ -100,6 +100,7 @@ SYMBOLS = {
     "lsm_volume": (_i32, [_vp, _vp, _pdbl]),
     "lsm_perimeter": (_i32, [_vp, _vp, _pdbl]),
     "lsm_extend_along_normals": (_i32, [_vp, _vp, _vp, _i32, _dbl, _vp, _dbl, _dbl]),
+    "lsm_field_csg": (_i32, [_vp, _vp, _vp, _i32]),
     "lsm_max_abs_diff": (_i32, [_vp, _vp, _vp, _pdbl]),
 }
 

@@ -783,6 +783,54 @@ def perimeter(phi) -> float:
     return out.value
 
 
+def _csg(dst: MeshField, src: Optional[MeshField], op: int) -> MeshField:
+    for f in (dst, src):
+        if f is not None and f.ncomp != 1:
+            raise ValueError("set operations need real-valued level-set fields")
+    if src is not None and src.mesh.n != dst.mesh.n:
+        raise ValueError("set operation between fields of different size")
+    ctx = dst._context()
+    L.check(L.lib().lsm_field_csg(ctx.handle, dst.device(), None if src is None else src.device(), op))
+    dst._mark_device_advanced()
+    return dst
+
+
+def union_(phi1: MeshField, phi2: MeshField) -> MeshField:
+    """``union!(phi1, phi2)``: phi1 = min(phi1, phi2) on the device (levelsetops.jl:253-259)."""
+    return _csg(phi1, phi2, 0)
+
+
+def intersect_(phi1: MeshField, phi2: MeshField) -> MeshField:
+    """``intersect!(phi1, phi2)``: phi1 = max(phi1, phi2) (levelsetops.jl:273-279)."""
+    return _csg(phi1, phi2, 1)
+
+
+def setdiff_(phi1: MeshField, phi2: MeshField) -> MeshField:
+    """``setdiff!(phi1, phi2)``: phi1 = max(phi1, -phi2) (levelsetops.jl:311-317)."""
+    return _csg(phi1, phi2, 2)
+
+
+def complement_(phi: MeshField) -> MeshField:
+    """``complement!(phi)``: phi = -phi (levelsetops.jl:293-298)."""
+    return _csg(phi, None, 3)
+
+
+def union(phi1: MeshField, phi2: MeshField) -> MeshField:
+    return union_(phi1.copy(), phi2)
+
+
+def intersect(phi1: MeshField, phi2: MeshField) -> MeshField:
+    return intersect_(phi1.copy(), phi2)
+
+
+def setdiff(phi1: MeshField, phi2: MeshField) -> MeshField:
+    return setdiff_(phi1.copy(), phi2)
+
+
+def complement(phi: MeshField) -> MeshField:
+    return complement_(phi.copy())
+
+
 def extend_along_normals(F: MeshField, phi: MeshField, nb_iters: int = 50, cfl: float = 0.45, frozen=None,
                          interface_band: float = 1.5, min_norm: float = 1.0e-14) -> MeshField:
     """``extend_along_normals!(F, phi; nb_iters, cfl, frozen, interface_band, min_norm)`` (velocityextension.jl:20-78) on the

@@ -1028,6 +1028,23 @@ int32_t lsm_extend_along_normals(lsm_ctx* ctx, lsm_field* F, lsm_field* phi, int
     return LSM_OK;
 }
 
+int32_t lsm_field_csg(lsm_ctx* ctx, lsm_field* dst, const lsm_field* src, int32_t op) {
+    if (!ctx || !dst) return fail(LSM_ERR_ARG, "null argument");
+    if (op < LSM_CSG_UNION || op > LSM_CSG_COMPLEMENT) return fail(LSM_ERR_ARG, "unknown set operation %d", op);
+    if (dst->ctx != ctx || dst->ncomp != 1 || dst->separable) return fail(LSM_ERR_ARG, "set operations need a real-valued field of this context");
+    if (op != LSM_CSG_COMPLEMENT) {
+        if (!src) return fail(LSM_ERR_ARG, "null argument");
+        if (src->ctx != ctx || src->ncomp != 1 || src->separable || src->ndim != dst->ndim || src->dtype != dst->dtype)
+            return fail(LSM_ERR_ARG, "set operation between incompatible fields");
+        for (int d = 0; d < dst->ndim; ++d) if (dst->nglob[d] != src->nglob[d]) return fail(LSM_ERR_ARG, "set operation between fields of different shape");
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_csg(dst->dtype == LSM_F64, dst->p, op == LSM_CSG_COMPLEMENT ? nullptr : src->p, dst->owned, op, ctx->stream));
+    ctx->cnt.kernel_launches += 1;
+    dst->version++; dst->halo_valid = false;
+    return LSM_OK;
+}
+
 int32_t lsm_max_abs_diff(lsm_ctx* ctx, const lsm_field* a, const lsm_field* b, double* out) {
     if (!ctx || !a || !b || !out) return fail(LSM_ERR_ARG, "null argument");
     if (a->ctx != ctx || b->ctx != ctx || a->dtype != b->dtype || a->ncomp != 1 || b->ncomp != 1 || a->owned != b->owned)

@@ -620,6 +620,38 @@ cudaError_t launch_signed_normals(int ndim, const View<T>& v, const double* h, d
 template cudaError_t launch_signed_normals<float>(int, const View<float>&, const double*, double, const unsigned char*, double, float*, long, cudaStream_t);
 template cudaError_t launch_signed_normals<double>(int, const View<double>&, const double*, double, const unsigned char*, double, double*, long, cudaStream_t);
 
+// levelsetops.jl:253-325: union! / intersect! / setdiff! / complement! as one pointwise pass.  Julia's min/max: NaN if either
+// operand is NaN; equal operands (signed zeros) resolve to -0.0 for min and +0.0 for max.
+template <class T> __device__ __forceinline__ T jl_min(T a, T b) {
+    if (a != a || b != b) return a + b;
+    if (a == b) return signbit(a) ? a : b;
+    return a < b ? a : b;
+}
+template <class T> __device__ __forceinline__ T jl_max(T a, T b) {
+    if (a != a || b != b) return a + b;
+    if (a == b) return signbit(a) ? b : a;
+    return a > b ? a : b;
+}
+template <class T>
+__global__ void __launch_bounds__(256) csg_kernel(T* __restrict__ dst, const T* __restrict__ src, const long n, const int op) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const T a = dst[i];
+        T r;
+        if (op == 3) r = -a;
+        else {
+            const T b = src[i];
+            r = op == 0 ? jl_min<T>(a, b) : (op == 1 ? jl_max<T>(a, b) : jl_max<T>(a, -b));
+        }
+        dst[i] = r;
+    }
+}
+cudaError_t launch_csg(int f64, void* dst, const void* src, long n, int op, cudaStream_t s) {
+    long grid = (n + 255) / 256; if (grid > 148L * 32) grid = 148L * 32; if (grid < 1) grid = 1;
+    if (f64) csg_kernel<double><<<(unsigned)grid, 256, 0, s>>>(static_cast<double*>(dst), static_cast<const double*>(src), n, op);
+    else csg_kernel<float><<<(unsigned)grid, 256, 0, s>>>(static_cast<float*>(dst), static_cast<const float*>(src), n, op);
+    return cudaGetLastError();
+}
+
 // K6: max |a - b| (bit-pattern max, NaN wins)
 template <class T>
 __global__ void __launch_bounds__(256) max_abs_diff_kernel(const T* __restrict__ a, const T* __restrict__ b, long n, unsigned long long* out) {

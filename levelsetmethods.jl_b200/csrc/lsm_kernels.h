@@ -19,6 +19,7 @@ cudaError_t launch_transpose(int f64, bool to_soa, const void* src, void* dst, l
 template <class T> cudaError_t launch_getindex(int ndim, const View<T>& v, const int* d_idx, int count, double* d_out, cudaStream_t s);
 template <class T> cudaError_t launch_measure(int ndim, bool perimeter, const View<T>& v, const double* h, double* d_partials, int nblocks, double* d_out, cudaStream_t s);
 template <class T> cudaError_t launch_signed_normals(int ndim, const View<T>& v, const double* h, double min_norm, const unsigned char* d_frozen, double band, T* a, long cstride, cudaStream_t s);
+cudaError_t launch_csg(int f64, void* dst, const void* src, long n, int op, cudaStream_t s);
 cudaError_t launch_max_abs_diff(int f64, const void* a, const void* b, long n, unsigned long long* out, cudaStream_t s);
 
 // lsm_tiled.cu (performance kernels).  Returns cudaErrorNotSupported when the configuration is

@@ -257,4 +257,15 @@ function extend_along_normals!(F::LSM.MeshField, ϕ::LSM.MeshField; nb_iters::In
     return F
 end
 
+# set operations on device fields (src/levelsetops.jl:253-325): 0 union!, 1 intersect!, 2 setdiff!, 3 complement!
+function csg!(d1::DeviceField, d2::Union{DeviceField, Nothing}, op::Integer; ctx::Context = default_context())
+    check(ccall((:lsm_field_csg, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32),
+                ctx.handle, d1.handle, d2 === nothing ? C_NULL : d2.handle, op))
+    return d1
+end
+Base.union!(a::DeviceField, b::DeviceField) = csg!(a, b, 0)
+Base.intersect!(a::DeviceField, b::DeviceField) = csg!(a, b, 1)
+Base.setdiff!(a::DeviceField, b::DeviceField) = csg!(a, b, 2)
+complement!(a::DeviceField) = csg!(a, nothing, 3)
+
 end # module

@@ -701,6 +701,19 @@ inline Idx mkidx(const int32_t* I, int nd) {
 
 }  // namespace
 
+namespace {
+template <class T> T jl_min(T a, T b) { if (a != a || b != b) return a + b; if (a == b) return std::signbit(a) ? a : b; return a < b ? a : b; }   // Base.min
+template <class T> T jl_max(T a, T b) { if (a != a || b != b) return a + b; if (a == b) return std::signbit(a) ? b : a; return a > b ? a : b; }   // Base.max
+template <class T> void csg_impl(T* d, const T* s, int64_t n, int op) {
+    for (int64_t i = 0; i < n; ++i) {
+        if (op == 0) d[i] = jl_min<T>(d[i], s[i]);            // levelsetops.jl:257
+        else if (op == 1) d[i] = jl_max<T>(d[i], s[i]);       // :277
+        else if (op == 2) d[i] = jl_max<T>(d[i], -s[i]);      // :315
+        else d[i] = -d[i];                                    // :296
+    }
+}
+}  // namespace
+
 extern "C" {
 
 void orc_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
@@ -836,6 +849,11 @@ void orc_eikonal_s0(const orc_field* phi0, double* out) {
             out[l++] = double(v) / std::sqrt(double(T(v * v)) + dx * dx);     // v / sqrt(v^2 + Δx^2)
         }
     });
+}
+
+void orc_csg(int dtype, void* dst, const void* src, int64_t n, int op) {
+    if (dtype == ORC_F64) csg_impl<double>(static_cast<double*>(dst), static_cast<const double*>(src), n, op);
+    else csg_impl<float>(static_cast<float*>(dst), static_cast<const float*>(src), n, op);
 }
 
 int orc_extend_along_normals(const orc_field* phi, void* F, int nb_iters, double cfl, const uint8_t* frozen, double band, double min_norm) {

@@ -123,6 +123,10 @@ int    orc_integrate(const orc_field* desc, int integrator, double cfl, void* ph
 int    orc_extend_along_normals(const orc_field* phi, void* F, int nb_iters, double cfl, const uint8_t* frozen,
                                 double interface_band, double min_norm);
 
+/* levelsetops.jl:253-325 : union! (0) / intersect! (1) / setdiff! (2) / complement! (3) on raw value arrays of `dtype`;
+ * Julia min/max semantics (NaN propagates, min(0.0,-0.0) = -0.0). */
+void   orc_csg(int dtype, void* dst, const void* src, int64_t n, int op);
+
 #ifdef __cplusplus
 }
 #endif

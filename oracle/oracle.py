@@ -90,6 +90,7 @@ def lib():
         L.orc_stage.argtypes = [fp, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, tp, C.c_int, dbl, dbl,
                                 C.POINTER(dbl)]
         L.orc_stage.restype = C.c_int
+        L.orc_csg.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]; L.orc_csg.restype = None
         L.orc_extend_along_normals.argtypes = [fp, C.c_void_p, C.c_int, dbl, C.c_void_p, dbl, dbl]; L.orc_extend_along_normals.restype = C.c_int
         L.orc_nstages.argtypes = [C.c_int]; L.orc_nstages.restype = C.c_int
         L.orc_advance.argtypes = [fp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, tp, C.c_int, dbl, dbl]
@@ -359,3 +360,12 @@ def extend_along_normals(F: np.ndarray, phi: Field, nb_iters=50, cfl=0.45, froze
     if rc:
         raise ValueError("invalid extend_along_normals arguments")
     return F
+
+
+def csg(op: str, a: np.ndarray, b=None) -> np.ndarray:
+    """``union!`` / ``intersect!`` / ``setdiff!`` / ``complement!`` (levelsetops.jl:253-325) on value arrays; returns a new array."""
+    code = {"union": 0, "intersect": 1, "setdiff": 2, "complement": 3}[op]
+    out = np.array(a, order="F", copy=True)
+    src = None if b is None else np.asfortranarray(b, dtype=out.dtype)
+    lib().orc_csg(F64 if out.dtype == np.float64 else F32, out.ctypes.data, None if src is None else src.ctypes.data, out.size, code)
+    return out

@@ -316,3 +316,17 @@ def test_extend_along_normals_reference_tests(O):
     out = O.extend_along_normals(F0.copy(order="F"), f, nb_iters=3)
     band = np.abs(f.vals) <= 1.5 * d
     assert np.array_equal(out[band], F0[band]) and not np.array_equal(out[~band], F0[~band])
+
+
+# ---- src/levelsetops.jl:253-325 : set operations, Julia min/max semantics ----
+def test_csg_semantics(O):
+    a = np.array([1.0, -2.0, 0.0, -0.0, np.nan, 3.0, 0.5])
+    b = np.array([0.5, -1.0, -0.0, 0.0, 1.0, np.nan, 0.5])
+    u, i, d, c = O.csg("union", a, b), O.csg("intersect", a, b), O.csg("setdiff", a, b), O.csg("complement", a)
+    assert np.array_equal(u[[0, 1, 6]], [0.5, -2.0, 0.5]) and np.isnan(u[4]) and np.isnan(u[5])
+    assert np.signbit(u[2]) and np.signbit(u[3])                 # min(0.0, -0.0) == -0.0 either way round
+    assert np.array_equal(i[[0, 1, 6]], [1.0, -1.0, 0.5]) and not np.signbit(i[2]) and not np.signbit(i[3])
+    assert np.array_equal(d[[0, 1, 6]], [1.0, 1.0, 0.5]) and np.isnan(d[4]) and np.isnan(d[5])
+    assert np.array_equal(c[[0, 1, 6]], [-1.0, 2.0, -0.5]) and np.signbit(c[2]) and not np.signbit(c[3])
+    # test/test-levelsetops.jl style identity: a \ b == a ∩ complement(b)
+    assert np.array_equal(O.csg("setdiff", a[:4], b[:4]), O.csg("intersect", a[:4], O.csg("complement", b[:4])))
