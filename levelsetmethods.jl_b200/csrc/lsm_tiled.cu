@@ -127,14 +127,20 @@ __device__ __forceinline__ double absmax5(double a, double b, double c, double d
 //   G1 = 5/6 e2 - 1/3 e1 ; G2 = 2 e3 + e2 ; G3 = 2 e3 - 1/2 e4     (6 and 3 folded in)
 // The floor 1e-70 replaces 4e-99*h^2 (which would underflow in the product form).  It only matters
 // where every |d| < ~1e-26, i.e. on numerically flat data, where the result is O(|d|) either way.
+// The five Float64 constants of the evaluation that do not fit an instruction immediate.  They travel in the kernel
+// parameters (constant bank): as literals the compiler re-materialises them with 10 UMOV per node, from the constant bank
+// it takes 3 uniform loads.
+struct WenoK { double c133, c56, cm13, e6, fl, pad; };
+inline WenoK weno_constants() { return {13.0 / 3.0, 5.0 / 6.0, -1.0 / 3.0, 4.0e-6, 1.0e-70, 0.0}; }
+
 template <class T>
-__device__ __forceinline__ double weno5_up(T q0, T q1, T q2, T q3, T q4, T q5) {
+__device__ __forceinline__ double weno5_up(const WenoK& K, T q0, T q1, T q2, T q3, T q4, T q5) {
     const double d0 = double(T(q1 - q0)), d1 = double(T(q2 - q1)), d2 = double(T(q3 - q2)),
                  d3 = double(T(q4 - q3)), d4 = double(T(q5 - q4));
     const double e1 = d1 - d0, e2 = d2 - d1, e3 = d3 - d2, e4 = d4 - d3;
     const double m = absmax5(d0, d1, d2, d3, d4);
-    const double eps = fma(4.0e-6, m * m, 1.0e-70);
-    const double c133 = 13.0 / 3.0;
+    const double eps = fma(K.e6, m * m, K.fl);
+    const double c133 = K.c133;
     const double t1a = e2 - e1, t1b = e3 - e2, t1c = e4 - e3;
     const double t2a = fma(3.0, e2, -e1), t2b = e2 + e3, t2c = fma(-3.0, e3, e4);
     const double b1 = fma(t2a, t2a, fma(c133, t1a * t1a, eps));
@@ -143,7 +149,7 @@ __device__ __forceinline__ double weno5_up(T q0, T q1, T q2, T q3, T q4, T q5) {
     const double p12 = b1 * b2, p13 = b1 * b3, p23 = b2 * b3;
     const double w1 = p23 * p23, w2 = p13 * p13, w3 = p12 * p12;
     const double den = fma(3.0, w3, fma(6.0, w2, w1));
-    const double G1 = fma(5.0 / 6.0, e2, (-1.0 / 3.0) * e1);
+    const double G1 = fma(K.c56, e2, K.cm13 * e1);
     const double G2 = fma(2.0, e3, e2);
     const double G3 = fma(2.0, e3, -0.5 * e4);
     const double num = fma(w3, G3, fma(w2, G2, w1 * G1));
@@ -156,7 +162,7 @@ __device__ __forceinline__ double weno5_up(T q0, T q1, T q2, T q3, T q4, T q5) {
 // lies in [4e-6, ~1e2], the weights in [1e-22, 1e8], and eps = 1e-6*max(v^2) becomes the exact constant 4e-6
 // (flat data: max|d| = 0 -> all b_k equal -> result d2 = 0, finite).
 template <>
-__device__ __forceinline__ double weno5_up<float>(float q0, float q1, float q2, float q3, float q4, float q5) {
+__device__ __forceinline__ double weno5_up<float>(const WenoK&, float q0, float q1, float q2, float q3, float q4, float q5) {
     const float d0 = q1 - q0, d1 = q2 - q1, d2 = q3 - q2, d3 = q4 - q3, d4 = q5 - q4;
     const float e1 = d1 - d0, e2 = d2 - d1, e3 = d3 - d2, e4 = d4 - d3;
     const float m = fmaxf(fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fmaxf(fabsf(d2), fabsf(d3))), fabsf(d4));
@@ -236,6 +242,7 @@ struct AuxList {
     int first[4];          // first aux index of term k (-1: not staged)
     int p0;                // aux index of phi^n / corr (-1: none)
     const void* src[8];    // box pointers (no ghost planes before the first owned node; same strides as the state)
+    WenoK wk;              // see WenoK
 };
 
 // Ghost index -> stored index for the boundary conditions that are pure index maps with weight 1
@@ -533,7 +540,7 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                             // s from the sign bits (integer ops instead of 8 DSETP): when u*g == 0 the reference takes the plus-biased
                             // stencil but multiplies it by zero, so either ordering yields the same 0 contribution (a == 0).
                             const int s = ((__double2hiint(u) ^ ghi) >> 31) | 1;                 // = sign(u*g); upwind-ordered sampling: q_k = phi[i - s*(3-k)]
-                            const double w = weno5_up<T>(up(d, -3, s), up(d, -2, s), up(d, -1, s), qc, up(d, 1, s), up(d, 2, s));
+                            const double w = weno5_up<T>(A.wk, up(d, -3, s), up(d, -2, s), up(d, -1, s), qc, up(d, 1, s), up(d, 2, s));
                             const double a = fabs(u) * (fabs(g) * ih[d]);
                             H = d == 0 ? a * w : fma(a, w, H);
                         }
@@ -809,7 +816,7 @@ cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, 
     if (!stage_tiled_supported<T>(ndim, P)) return cudaErrorNotSupported;
     if (P.r1 <= P.r0) return cudaSuccess;
     AuxList A{};
-    A.n = 0; A.p0 = -1;
+    A.n = 0; A.p0 = -1; A.wk = weno_constants();
     int mask = 0;
     for (int k = 0; k < 4; ++k) A.first[k] = -1;
     for (int k = 0; k < P.nterms; ++k) {

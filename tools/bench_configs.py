@@ -30,7 +30,7 @@ def peak():
         return 6650.0
 
 
-def run(name, case, integ, balg, steps, warmup=3):
+def run(name, case, integ, balg, steps, warmup=3, reps=5):
     ctx = m.default_context()
     phi = case.engine_field(m)
     terms = case.engine_terms(m, phi)
@@ -47,21 +47,25 @@ def run(name, case, integ, balg, steps, warmup=3):
         return t_out.value
 
     t = go(warmup, 0.0) if warmup > 0 else 0.0
-    ctx.set_option(L.OPT_TIME_STAGES, 1)
-    ctx.sync(); ctx.reset_counters()
-    ctx.event_record(0)
-    t = go(steps, t)
-    ctx.event_record(1)
-    ms = ctx.event_elapsed_ms(0, 1)
-    cnt = ctx.counters()
-    ctx.set_option(L.OPT_TIME_STAGES, 0)
+    # median of `reps` timed runs of `steps` steps each (device time, CUDA events on the library stream)
+    runs = []
+    for _ in range(max(reps, 1)):
+        ctx.set_option(L.OPT_TIME_STAGES, 1)
+        ctx.sync(); ctx.reset_counters()
+        ctx.event_record(0)
+        t = go(steps, t)
+        ctx.event_record(1)
+        runs.append((ctx.event_elapsed_ms(0, 1), ctx.counters()))
+        ctx.set_option(L.OPT_TIME_STAGES, 0)
+    runs.sort(key=lambda r: r[0])
+    ms, cnt = runs[len(runs) // 2]
     nodes = int(np.prod(case.n))
     ups = nodes * steps / (ms * 1e-3)
     stage_ms = cnt["sum_stage_ms"] / max(cnt["timed_stages"], 1)
     nst = integ.nstages
     ach = balg / nst * nodes / (stage_ms * 1e-3) / 1e9
     out = {"config": name, "grid": list(case.n), "dtype": np.dtype(case.dtype).name, "integrator": type(integ).__name__,
-           "steps": steps, "ms_per_step": ms / steps, "cell_updates_per_s": ups, "avg_stage_launch_ms": stage_ms,
+           "steps": steps, "reps": len(runs), "ms_per_step_min_max": [runs[0][0] / steps, runs[-1][0] / steps], "ms_per_step": ms / steps, "cell_updates_per_s": ups, "avg_stage_launch_ms": stage_ms,
            "algorithmic_bytes_per_update": balg, "achieved_gbs": ach, "peak_gbs": peak(), "frac": ach / peak(),
            "step_frac_of_roofline": ups * balg / 1e9 / peak(), "kernel_launches": cnt["kernel_launches"], "cfl_passes": cnt["cfl_passes"]}
     print(json.dumps(out), flush=True)
@@ -74,6 +78,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--skip", default="")
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--kernel", type=int, default=0)
     a = ap.parse_args()
     m.default_context().set_option(L.OPT_KERNEL, a.kernel)
@@ -92,7 +97,7 @@ def main():
     for name, mk, integ, balg in cfgs:
         if (a.only and not name.startswith(a.only)) or (a.skip and name.startswith(a.skip)):
             continue
-        run(name, mk(), integ, balg, a.steps if "128^2" not in name else 10 * a.steps, a.warmup)
+        run(name, mk(), integ, balg, a.steps if "128^2" not in name else 10 * a.steps, a.warmup, a.reps)
 
 
 if __name__ == "__main__":
