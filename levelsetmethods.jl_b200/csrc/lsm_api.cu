@@ -333,7 +333,10 @@ int32_t run_stage_t(lsm_ctx* c, lsm_field* in, lsm_field* p0, lsm_field* out, ls
             bool remap = true;      // the fused variant exists for the index-remap instantiation only
             for (int d = 0; d < 3; ++d) for (int sd = 0; sd < 2; ++sd) if (P.in.bc[d][sd].kind == BC_EXTRAP && P.in.bc[d][sd].P > 0) remap = false;
             if (!remap) goto no_fuse;
-            P.cfl_out = c->d_scalar + 1; P.cfl_g = c->fuse_req.g_next; P.cfl_tau = c->fuse_req.tau;
+            P.cfl_out = c->d_scalar + 1; P.cfl_g = c->fuse_req.g_next;
+            // the kernel's cheap estimate is sum_d |u_d| (|g_stage| / h_d), which it already forms for the Hamiltonian; the bound
+            // tau on sum_d |u_d g_next| / h_d therefore becomes tau |g_stage / g_next| (inf / NaN -> no candidates -> full pass)
+            P.cfl_tau = (1.0 - 1e-13) * c->fuse_req.tau * std::fabs((t0.scaled ? t0.g : 1.0) / c->fuse_req.g_next);
             CU(cudaMemsetAsync(c->d_scalar + 1, 0, 8, c->stream));
             c->fused.valid = true; c->fused.field = terms[0].field; c->fused.version = terms[0].field->version; c->fused.g = c->fuse_req.g_next;
         }

@@ -64,7 +64,7 @@ struct StageParams {
     // stage also reduces max_nodes sum_d |u_d * cfl_g| / h_d.  Exact: only nodes whose cheap estimate reaches cfl_tau (a lower
     // bound of the new maximum derived from the previous exact maximum) evaluate the reference expression with true divisions.
     unsigned long long* cfl_out;   // device scalar (IEEE bits, atomicMax) or nullptr
-    double cfl_g, cfl_tau;
+    double cfl_g, cfl_tau;         // g(t_next); candidate bound on the kernel's estimate sum_d |u_d| |g_stage| / h_d
     TermDev terms[4];
 };
 

@@ -535,13 +535,14 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
 #pragma unroll
                         for (int d = 0; d < NDIM; ++d) {
                             const double u = coef_raw(tm, kk, d, kc);             // velocity before the time factor g(t)
-                            if (do_cfl) { uu[d] = u; sest = fma(fabs(u), fabs(P.cfl_g) * ih[d], sest); }
+                            if (do_cfl) uu[d] = u;
                             // v = u*g; v > 0 selects the minus-biased stencil.  sign(v) = sign(u)*sign(g); |v|/h = |u| * (|g|/h)
                             // s from the sign bits (integer ops instead of 8 DSETP): when u*g == 0 the reference takes the plus-biased
                             // stencil but multiplies it by zero, so either ordering yields the same 0 contribution (a == 0).
                             const int s = ((__double2hiint(u) ^ ghi) >> 31) | 1;                 // = sign(u*g); upwind-ordered sampling: q_k = phi[i - s*(3-k)]
                             const double w = weno5_up<T>(A.wk, up(d, -3, s), up(d, -2, s), up(d, -1, s), qc, up(d, 1, s), up(d, 2, s));
                             const double a = fabs(u) * (fabs(g) * ih[d]);
+                            if (do_cfl) sest = d == 0 ? a : sest + a;       // = sum_d |u_d| |g_stage| / h_d, compared with tau |g_stage / g_next|
                             H = d == 0 ? a * w : fma(a, w, H);
                         }
                         if (do_cfl && !(sest < P.cfl_tau)) {
