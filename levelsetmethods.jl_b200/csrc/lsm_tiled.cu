@@ -43,7 +43,8 @@ namespace {
 #define LSM_MINB_2D 4      // 2-D blocks process a single tile (load, wait, compute): latency bound, so favour resident blocks
 #endif
 #ifndef LSM_MINB_EIK
-#define LSM_MINB_EIK 3    // Eikonal kernel: latency-bound at 16 warps/SM (ncu: 'wait' + short-scoreboard stalls lead); 3 blocks of 74 KB fit
+#define LSM_MINB_EIK 3    // Eikonal kernel: latency-bound at 16 warps/SM (ncu: 'wait' + short-scoreboard stalls lead); 3 blocks of 74 KB fit.
+                          // Also the Float32 advection kernels (45 KB each; the fused-CFL variant otherwise takes 84 registers -> 2 blocks)
 #endif
 constexpr int HAL = 3;           // WENO5 reach; every term's stencil fits in it
 
@@ -269,7 +270,8 @@ __device__ __forceinline__ int remap_index(int i, int n, int kind_lo, int kind_h
 // (order, coefficients) are runtime data, applied one after the other like the reference
 // (x = base; x -= c*H_1; x -= c*H_2; ..., timestepping.jl:128-202).
 template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL, int TX, int TY, int NY, int MINB, int TK>
-__global__ void __launch_bounds__(TX * TY, (NDIM == 2 ? LSM_MINB_2D : (MASK == M_EIK && TK >= 0 ? LSM_MINB_EIK : MINB)))
+__global__ void __launch_bounds__(TX * TY, (NDIM == 2 ? LSM_MINB_2D
+                                                   : ((MASK == M_EIK && TK >= 0) || (sizeof(T) == 4 && MASK == M_ADV_WENO && NTS == 1) ? LSM_MINB_EIK : MINB)))
 stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ AuxList A, const __grid_constant__ TmaMaps M, const int cz) {
     using G = TileGeom<T, NDIM, TX, TY, NY>;
     constexpr int RING = G::RING;

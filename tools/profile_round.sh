@@ -13,3 +13,8 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
 if [ "$1" != "nofull" ]; then
 ncu --set full --clock-control none --import-source on -k regex:stage_tiled -s 10 -c 3 -f -o $O/prof_c3 $B > $O/ncu_full.log 2>&1
 fi
+# one RK step of every BASELINE configuration under ncu (sections, not --set full): every specialised kernel once
+K="python tools/bench_configs.py --steps 1 --warmup 0 --reps 1 --skip C1"
+$K > $O/cfg1.log 2>&1 && ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section ComputeWorkloadAnalysis --section SchedulerStats \
+    --section WarpStateStats --section LaunchStats --section Occupancy --clock-control none -k regex:stage_tiled -c 30 --csv --page raw \
+    --log-file $O/ncu_kernels.csv $K > $O/ncu_kernels.log 2>&1
