@@ -152,6 +152,14 @@ def _small_cases():
             "eik_frozen": [dict(kind="eikonal", frozen=True)],
             "eik_live": [dict(kind="eikonal", frozen=False)],
             "three": [dict(kind="normal", field=v), dict(kind="advection", field=u), dict(kind="curvature", const=-0.01)],
+            # two-term lists: the BASELINE orders run the static-signature kernels (C5: normal+adv fields, C2: adv field + const
+            # curvature); the reversed orders / other coefficient kinds must take the runtime-dispatch kernels of the same masks
+            "normal_adv": [dict(kind="normal", field=v), dict(kind="advection", field=u)],
+            "adv_normal": [dict(kind="advection", field=u), dict(kind="normal", field=v)],
+            "normalc_adv": [dict(kind="normal", const=0.6), dict(kind="advection", field=u)],
+            "adv_curvc": [dict(kind="advection", field=u), dict(kind="curvature", const=-0.03)],
+            "curvc_adv": [dict(kind="curvature", const=-0.03), dict(kind="advection", field=u)],
+            "adv_curvf": [dict(kind="advection", field=u), dict(kind="curvature", field=b)],
         }
         for i, (tn, ts) in enumerate(termsets.items()):
             bc = tuple(bcs[(i + d) % len(bcs)] for d in range(N))
