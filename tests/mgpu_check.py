@@ -78,6 +78,39 @@ def main():
                 ok &= good
                 print(f"[{'ok' if good else 'FAIL'}] {name} ({world} ranks, overlap={overlap}): bitwise == 1-GPU: {bit}; "
                       f"max-abs vs oracle {d:.2e}; steps {eq.steps_taken}", flush=True)
+    # ---- "next" rows on a decomposed field: device volume / perimeter (all-reduced), set operations, velocity extension
+    m.set_default_context(ctx)
+    n3 = (nc, nc + 2, 16 * world + 3)
+    lc3, hc3 = (-1, -1, -1), (1, 1, 1)
+    X = H.coords(lc3, hc3, n3)
+    a0 = H.bcast(np.sqrt((X[0] - 0.1) ** 2 + X[1] ** 2 + X[2] ** 2) - 0.6, n3)
+    b0 = H.bcast(np.maximum(np.abs(X[0]), np.maximum(np.abs(X[1]), np.abs(X[2] - 0.2))) - 0.45, n3)
+    F0 = H.bcast(np.sin(2 * X[0]) + X[1] * X[2], n3)
+
+    def run_next(c):
+        g = m.CartesianGrid(lc3, hc3, n3)
+        a = m.MeshField(a0.copy(order="F"), g, bc=m.NeumannBC(), ctx=c)
+        b = m.MeshField(b0.copy(order="F"), g, ctx=c)
+        m.setdiff_(a, b)
+        vol, per = m.volume(a), m.perimeter(a)
+        F = m.MeshField(F0.copy(order="F"), g, ctx=c)
+        m.extend_along_normals(F, a, nb_iters=10)
+        return vol, per, np.ascontiguousarray(a.peek()), np.ascontiguousarray(F.peek()), a.local_range
+
+    vol, per, av, Fv, rng = run_next(ctx)
+    parts = [None] * world
+    dist.gather_object((rng, av, Fv), parts if rank == 0 else None, dst=0)
+    if rank == 0:
+        parts.sort(key=lambda q: q[0][0])
+        a_full = np.concatenate([p[1] for p in parts], axis=-1)
+        F_full = np.concatenate([p[2] for p in parts], axis=-1)
+        m.set_default_context(solo)
+        vol1, per1, a1, F1, _ = run_next(solo)
+        good = (np.array_equal(a_full, a1) and abs(vol - vol1) <= 1e-12 * abs(vol1) and abs(per - per1) <= 1e-12 * abs(per1)
+                and float(np.abs(F_full - F1).max()) <= 1e-12)
+        ok &= good
+        print(f"[{'ok' if good else 'FAIL'}] setdiff! + volume/perimeter + extend_along_normals! ({world} ranks): CSG bitwise {np.array_equal(a_full, a1)}; "
+              f"volume {vol:.15g} vs {vol1:.15g}; perimeter {per:.15g} vs {per1:.15g}; extension max-abs diff {float(np.abs(F_full - F1).max()):.2e}", flush=True)
     res = [ok]
     dist.broadcast_object_list(res, src=0)
     if rank == 0:
