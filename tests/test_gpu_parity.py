@@ -5,6 +5,7 @@ cut-cell classification.  The strict generic kernel is additionally required to 
 rounding level (<= 1e-13 relative) on every term / BC / dimension / dtype combination.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -218,6 +219,25 @@ def test_config_parity_100_steps(m, O, name, mk, dtype):
     assert n >= 0.9 * steps
     d = check_parity(a, b, 1e-10 if dtype == np.float64 else 1e-4)
     print(f"{name} {np.dtype(dtype).name}: {n} steps, max-abs diff {d:.3e}")
+
+
+def test_against_committed_vectors(m):
+    """The engine against tests/golden/oracle_vectors.npz (committed oracle outputs for small instances of C1..C5, f64 and
+    f32): catches a change that moves the oracle and the engine together."""
+    import importlib.util
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_oracle_vectors", os.path.join(gdir, "make_oracle_vectors.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    gold = np.load(os.path.join(gdir, "oracle_vectors.npz"))
+    for name, (mk, integ, steps) in gen.CASES.items():
+        for dtype, tag in ((np.float64, "f64"), (np.float32, "f32")):
+            case = mk(dtype)
+            tf, n = gold[f"{name}_{tag}_tf_steps"]
+            phi = case.engine_field(m)
+            eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator={"RK2": m.RK2, "RK3": m.RK3}[integ]())
+            m.integrate(eq, float(tf))
+            assert eq.steps_taken == int(n), (name, tag)
+            check_parity(gold[f"{name}_{tag}"], eq.state.peek(), 1e-10 if dtype == np.float64 else 1e-4)
 
 
 def test_c4_rk2_reference_default(m, O):

@@ -3,10 +3,16 @@ test-suite and doctests hold for the dense-grid integration path (SURVEY.md §8c
 
 Each test names the reference test it re-expresses (paths relative to /root/reference).
 """
+import json
 import math
+import os
 
 import numpy as np
 import pytest
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KNOWN = json.load(open(os.path.join(GOLDEN, "reference_known_answers.json")))      # numbers the reference itself states, with citations
 
 
 def mk(O, f, lc, hc, n, bc=None, dtype=np.float64):
@@ -18,9 +24,10 @@ def mk(O, f, lc, hc, n, bc=None, dtype=np.float64):
 
 # ---- src/levelsetops.jl:14-25 and :126-137 (jldoctest scalars) : the only stored numbers ----
 def test_doctest_volume_perimeter_bitexact(O):
-    f = mk(O, lambda x, y: np.sqrt(x * x + y * y) - 0.5, (-1, -1), (1, 1), (200, 200))
-    assert f.volume() == 0.7854362890190668
-    assert f.perimeter() == 3.1426415491430384
+    k = KNOWN["doctest_circle_200x200"]
+    f = mk(O, lambda x, y: np.sqrt(x * x + y * y) - k["radius"], k["lc"], k["hc"], tuple(k["n"]))
+    assert f.volume() == k["volume"] == 0.7854362890190668
+    assert f.perimeter() == k["perimeter"] == 3.1426415491430384
 
 
 # ---- test/test-meshes.jl:6-14 ----
@@ -72,9 +79,9 @@ def test_extrapolation_getindex(O):
 def test_extrapolation_weight_table():
     """SURVEY.md §8a table for w_j(k,P) (boundaryconditions.jl:90-97) via ghost reads of unit vectors."""
     import oracle as O
-    table = {(0, 1): [1], (1, 1): [2, -1], (1, 2): [3, -2], (1, 3): [4, -3],
-             (2, 1): [3, -3, 1], (2, 2): [6, -8, 3], (2, 3): [10, -15, 6],
-             (3, 1): [4, -6, 4, -1], (3, 2): [10, -20, 15, -4], (3, 3): [20, -45, 36, -10]}
+    wt = KNOWN["lagrange_extrapolation_weights"]
+    table = {(P, k): wt[f"P{P}"][f"k{k}"] for P in range(4) for k in (1, 2, 3)}
+    assert table[(2, 3)] == [10, -15, 6] and table[(3, 2)] == [10, -20, 15, -4]
     n = 8
     for (P, k), w in table.items():
         for j, wj in enumerate(w):
@@ -330,3 +337,27 @@ def test_csg_semantics(O):
     assert np.array_equal(c[[0, 1, 6]], [-1.0, 2.0, -0.5]) and np.signbit(c[2]) and not np.signbit(c[3])
     # test/test-levelsetops.jl style identity: a \ b == a ∩ complement(b)
     assert np.array_equal(O.csg("setdiff", a[:4], b[:4]), O.csg("intersect", a[:4], O.csg("complement", b[:4])))
+
+
+# ---- tests/golden/oracle_vectors.npz : the oracle pinned against its own committed outputs ----
+def test_oracle_golden_vectors(O):
+    """Regression pin: the oracle must keep reproducing the committed vectors of the five BASELINE configurations (small
+    instances, f64 and f32; generated by tests/golden/make_oracle_vectors.py).  Same compiler flags -> equality; the
+    tolerance only allows for a different libm (sin/cos in the input fields)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_oracle_vectors", os.path.join(GOLDEN, "make_oracle_vectors.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    gold = np.load(os.path.join(GOLDEN, "oracle_vectors.npz"))
+    O.set_threads(4)
+    for name in gen.CASES:
+        for dtype, tag in ((np.float64, "f64"), (np.float32, "f32")):
+            v, tf, n = gen.run(name, dtype)
+            g = gold[f"{name}_{tag}"]
+            assert g.dtype == v.dtype and g.shape == v.shape
+            assert gold[f"{name}_{tag}_tf_steps"][1] == n
+            assert np.abs(v.astype(np.float64) - g.astype(np.float64)).max() <= (1e-13 if dtype == np.float64 else 1e-6), (name, tag)
+    # the periodic wrap pairs of the reference (boundaryconditions.jl:107-119)
+    k = KNOWN["periodic_wrap"]
+    f = O.Field(np.arange(1.0, k["n"] + 1), (0,), (1,), bc=O.PERIODIC)
+    for i, j in k["pairs"]:
+        assert f[i] == float(j)
