@@ -70,6 +70,7 @@ struct lsm_ctx {
     struct { bool on = false; double g_next = 0, tau = 0; } fuse_req;
     struct { bool valid = false; const void* field = nullptr; uint64_t version = 0; double g = 0; } fused;
     int opt_fuse_cfl = 1;
+    int opt_graph = 1;          // lsm_integrate replays a captured CUDA graph of the stage launches on small grids
 };
 
 struct lsm_field {
@@ -116,6 +117,7 @@ int32_t ctx_common_init(lsm_ctx* c) {
     CU(cudaMalloc(&c->d_scalar, 64));
     CU(cudaMallocHost(&c->h_scalar, 64));
     if (getenv("LSM_B200_NO_FUSE_CFL")) c->opt_fuse_cfl = 0;
+    if (getenv("LSM_B200_NO_GRAPH")) c->opt_graph = 0;
     return LSM_OK;
 }
 
@@ -541,7 +543,7 @@ int32_t lsm_ctx_create(int32_t device, lsm_ctx** out) {
     if (!c) return fail(LSM_ERR_OOM, "host allocation failed");
     c->device = device;
     int32_t rc = ctx_common_init(c);
-    if (rc != LSM_OK) { delete c; return rc; }
+    if (rc != LSM_OK) { lsm_ctx_destroy(c); return rc; }      // releases whatever was created; the error text is already set
     *out = c;
     return LSM_OK;
 }
@@ -568,11 +570,11 @@ int32_t lsm_ctx_create_rank(int32_t device, int32_t rank, int32_t nranks, const 
     if (!c) return fail(LSM_ERR_OOM, "host allocation failed");
     c->device = device; c->rank = rank; c->nranks = nranks;
     int32_t rc = ctx_common_init(c);
-    if (rc != LSM_OK) { delete c; return rc; }
+    if (rc != LSM_OK) { lsm_ctx_destroy(c); return rc; }
     ncclUniqueId id;
     std::memcpy(&id, id128, 128);
     ncclResult_t r = nccl().CommInitRank(&c->nccl_comm, nranks, id, rank);
-    if (r != ncclSuccess) { delete c; return fail(LSM_ERR_NCCL, "ncclCommInitRank failed: %s", nccl().GetErrorString(r)); }
+    if (r != ncclSuccess) { c->nccl_comm = nullptr; lsm_ctx_destroy(c); return fail(LSM_ERR_NCCL, "ncclCommInitRank failed: %s", nccl().GetErrorString(r)); }
     *out = c;
     return LSM_OK;
 }
@@ -613,6 +615,7 @@ int32_t lsm_set_option(lsm_ctx* c, int32_t option, int32_t value) {
         case LSM_OPT_CFL_CACHE: c->opt_cfl_cache = value != 0; c->cfl_cache.clear(); break;
         case LSM_OPT_OVERLAP: c->opt_overlap = value != 0; break;
         case LSM_OPT_FUSE_CFL: c->opt_fuse_cfl = value != 0; break;
+        case LSM_OPT_GRAPH: c->opt_graph = value != 0; break;
         default: return fail(LSM_ERR_ARG, "unknown option %d", option);
     }
     return LSM_OK;
@@ -888,12 +891,38 @@ int32_t lsm_integrate(lsm_ctx* ctx, int32_t integrator, double cfl, lsm_field* p
     int64_t steps = 0;
     bool finished = true;
     int32_t rc = LSM_OK;
+    // Launch-bound regime (small grids: a stage kernel lasts a few microseconds, comparable to its launch): when nothing but the
+    // state changes from step to step — single rank, RK2/RK3 (whose buffers do not rotate), terms without a time factor, no
+    // per-stage timing — the stage launches of one step are captured once into a CUDA graph and every later step with the same
+    // dt replays it (one graph launch instead of 2-3 kernel launches plus their host-side setup).
+    bool graph_ok = ctx->opt_graph && ctx->nranks == 1 && integrator != LSM_FORWARD_EULER && !ctx->opt_time &&
+                    phi->owned <= (1L << 22);
+    for (int k = 0; k < nterms && graph_ok; ++k) if (terms[k].tscale_kind != LSM_TS_NONE) graph_ok = false;
+    cudaGraphExec_t gexec = nullptr;
+    double gdt = 0.0;
+    lsm_counters gdelta{};          // counters of one captured step
+    uint64_t gver[3] = {0, 0, 0};   // version bumps of phi / buf1 / buf2 per step
     while (tc <= tf - jl_eps(tc)) {                                   // timestepping.jl:104
         if (max_steps >= 0 && steps >= max_steps) { finished = false; break; }
         double dt_cfl;
         rc = compute_cfl_impl(ctx, phi, terms, nterms, tc, nullptr, &dt_cfl);
         if (rc != LSM_OK) { finished = false; break; }
         const double dt = jl_min(jl_min(dt_max, cfl * dt_cfl), tf - tc);   // timestepping.jl:111
+        if (gexec && dt == gdt) {
+            cudaError_t ge = cudaGraphLaunch(gexec, ctx->stream);
+            if (ge != cudaSuccess) { rc = fail(LSM_ERR_CUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(ge)); finished = false; break; }
+            ctx->cnt.kernel_launches += gdelta.kernel_launches; ctx->cnt.stage_launches += gdelta.stage_launches;
+            phi->version += gver[0]; if (phi->buf1) phi->buf1->version += gver[1]; if (phi->buf2) phi->buf2->version += gver[2];
+            tc += dt;
+            ++steps;
+            continue;
+        }
+        // capture on the second step of the call (the first one has set every launch attribute and filled the CFL cache)
+        const bool capture = graph_ok && !gexec && steps >= 1;
+        lsm_counters before = ctx->cnt;
+        uint64_t vb[3] = {phi->version, phi->buf1 ? phi->buf1->version : 0, phi->buf2 ? phi->buf2->version : 0};
+        if (capture && cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); graph_ok = false; }
+        const bool capturing = capture && graph_ok;
         for (int s = 1; s <= nstages(integrator) && rc == LSM_OK; ++s) {
             if (s == nstages(integrator) && ctx->opt_fuse_cfl && ctx->opt_cfl_cache && nterms == 1 && terms[0].kind == LSM_TERM_ADVECTION &&
                 (terms[0].coef_kind == LSM_COEF_FIELD || terms[0].coef_kind == LSM_COEF_SEPARABLE) && terms[0].tscale_kind == LSM_TS_COS && (tc + dt) <= tf - jl_eps(tc + dt)) {
@@ -907,10 +936,32 @@ int32_t lsm_integrate(lsm_ctx* ctx, int32_t integrator, double cfl, lsm_field* p
             }
             rc = stage_impl(ctx, integrator, s, phi, terms, nterms, tc, dt, nullptr);
         }
+        if (capturing) {
+            cudaGraph_t graph = nullptr;
+            cudaError_t ge = cudaStreamEndCapture(ctx->stream, &graph);
+            if (ge == cudaSuccess && graph && rc == LSM_OK) ge = cudaGraphInstantiate(&gexec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc == LSM_OK && ge == cudaSuccess && gexec && cudaGraphLaunch(gexec, ctx->stream) == cudaSuccess) {
+                gdt = dt;
+                gdelta.kernel_launches = ctx->cnt.kernel_launches - before.kernel_launches;
+                gdelta.stage_launches = ctx->cnt.stage_launches - before.stage_launches;
+                gver[0] = phi->version - vb[0]; gver[1] = phi->buf1 ? phi->buf1->version - vb[1] : 0; gver[2] = phi->buf2 ? phi->buf2->version - vb[2] : 0;
+            } else {
+                // capture not possible here: nothing of this step has run yet — drop graph mode and run the step directly
+                // (an error raised while capturing is treated as "cannot capture": a real one recurs in the direct run)
+                cudaGetLastError();
+                if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+                graph_ok = false;
+                ctx->cnt = before;
+                rc = LSM_OK;
+                for (int s = 1; s <= nstages(integrator) && rc == LSM_OK; ++s) rc = stage_impl(ctx, integrator, s, phi, terms, nterms, tc, dt, nullptr);
+            }
+        }
         if (rc != LSM_OK) { finished = false; break; }
         tc += dt;
         ++steps;
     }
+    if (gexec) { cudaStreamSynchronize(ctx->stream); cudaGraphExecDestroy(gexec); }
     cudaStreamSynchronize(ctx->comm);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (t_out) *t_out = finished ? tf : tc;                           // timestepping.jl:120

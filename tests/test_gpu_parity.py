@@ -527,6 +527,35 @@ def test_csg_on_device(m, O, dtype):
     assert np.abs(eq.state.peek().astype(np.float64) - fo.vals.astype(np.float64)).max() <= (1e-10 if dtype == np.float64 else 1e-4)
 
 
+def test_graph_replay_is_invisible(m, O):
+    """Small grids: lsm_integrate replays a captured CUDA graph of one step's stage launches (LSM_OPT_GRAPH).  States, times,
+    step counts and launch counters must be identical with the option on and off, for RK3 and RK2, 2-D and 3-D, including a
+    final shorter step (different dt -> direct launches) and a second integrate! call on the same equation."""
+    ctx = m.default_context()
+    OPT_GRAPH = m._lib.OPT_GRAPH
+    for mk, integ in ((lambda: H.c1_circle_rotation(64), m.RK3), (lambda: H.c2_zalesak_curvature(96), m.RK2),
+                      (lambda: H.c5_normal_advection(24), m.RK3)):
+        res = []
+        for on in (1, 0):
+            ctx.set_option(OPT_GRAPH, on)
+            case = mk()
+            phi = case.engine_field(m)
+            eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=integ())
+            dt0 = 0.5 * m.compute_cfl(eq.terms, eq.state, 0.0)
+            ctx.reset_counters()
+            m.integrate(eq, dt0 * 17.3)               # 17 full steps + one shorter
+            n1 = eq.steps_taken
+            m.integrate(eq, dt0 * 25.0)
+            c = ctx.counters()
+            res.append((eq.state.peek().copy(), eq.t, n1, eq.steps_taken, c["kernel_launches"], c["stage_launches"]))
+        ctx.set_option(OPT_GRAPH, 1)
+        assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:], res[0][1:]
+        fo = mk().oracle_field()
+        O.integrate(fo, {m.RK3: O.RK3, m.RK2: O.RK2}[integ], mk().oracle_terms(), res[0][1])
+        # two integrate calls vs one oracle call to the same final time: the step sequences differ, so compare loosely
+        assert np.abs(res[0][0] - fo.vals).max() < 1e-3
+
+
 def test_counters_and_launch_accounting(m):
     ctx = m.default_context()
     case = H.c3_enright(32)
