@@ -96,7 +96,7 @@ typedef struct {
 /* options for lsm_set_option */
 enum {
     LSM_OPT_KERNEL = 0,       /* 0 auto (tiled where available), 1 force generic strict kernel, 2 force tiled */
-    LSM_OPT_TIME_STAGES = 1,  /* 1: bracket every stage kernel with CUDA events (adds a sync per stage)       */
+    LSM_OPT_TIME_STAGES = 1,  /* 1: bracket every stage launch with CUDA events, resolved at the next sync  */
     LSM_OPT_CFL_CACHE = 2,    /* 1 (default): reuse the CFL reduction while coefficient data/scale unchanged  */
     LSM_OPT_OVERLAP = 3,      /* 1 (default): overlap halo exchange with interior compute (multi-rank)        */
     LSM_OPT_FUSE_CFL = 4,     /* 1 (default): lsm_integrate lets the last RK stage reduce the next step's CFL maximum (time-scaled stored velocity) */
