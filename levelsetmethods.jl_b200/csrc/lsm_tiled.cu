@@ -199,6 +199,8 @@ __device__ __forceinline__ float div3(float x) {
 
 // Static term signature of the multi-term instantiations: TK packs the kind of term k in bits [3k, 3k+3)
 // (SK_* below; TK < 0: kinds are runtime data), COEFK packs its coefficient kind in bits [2k, 2k+2) (COEFK < 0: runtime).
+// static base modes of a launch (template parameter SB; -1 = runtime): BASE_* of lsm_dev.cuh plus the presence of out2
+enum : int { SB_IN = 0, SB_S2 = 1, SB_S3 = 2, SB_IN_OUT2 = 3, SB_P0 = 4 };
 enum : int { SK_ADV_WENO = 0, SK_ADV_UPWIND = 1, SK_NORMAL = 2, SK_CURV = 3, SK_EIK = 4 };
 __host__ __device__ constexpr int sig_kind(int TK, int k) { return TK < 0 || k < 0 ? -1 : ((TK >> (3 * k)) & 7); }
 __host__ __device__ constexpr int sig_coef(int COEFK, int k) { return COEFK < 0 || k < 0 ? -1 : ((COEFK >> (2 * k)) & 3); }
@@ -269,7 +271,7 @@ __device__ __forceinline__ int remap_index(int i, int n, int kind_lo, int kind_h
 // Fused stage kernel.  MASK = which term kinds the instantiation carries code for; the terms themselves
 // (order, coefficients) are runtime data, applied one after the other like the reference
 // (x = base; x -= c*H_1; x -= c*H_2; ..., timestepping.jl:128-202).
-template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL, int TX, int TY, int NY, int MINB, int TK>
+template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL, int TX, int TY, int NY, int MINB, int TK, int SB>
 __global__ void __launch_bounds__(TX * TY, (NDIM == 2 ? LSM_MINB_2D
                                                    : ((MASK == M_EIK && TK >= 0) || (sizeof(T) == 4 && MASK == M_ADV_WENO && NTS == 1) ? LSM_MINB_EIK : MINB)))
 stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ AuxList A, const __grid_constant__ TmaMaps M, const int cz) {
@@ -509,11 +511,17 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                     ps = fma(-0.5, minmod(cp, cc), dp);
                 };
 
+                // static base mode SB (see SB_* below): which RK combination this launch forms, whether phi^n / corr is staged (and in
+                // which aux slot) and whether a second accumulator is written are compile-time facts; SB < 0 reads them at run time
+                constexpr int SP0 = TK >= 0 ? sig_first(TK, COEFK, NTS, NDIM) : (COEFK == COEF_FIELD ? NDIM : 0);   // aux slot of phi^n (static kernels)
+                const int base = SB < 0 ? P.base : (SB == SB_IN || SB == SB_IN_OUT2 ? BASE_IN : SB == SB_S2 ? BASE_RK3_S2 : SB == SB_S3 ? BASE_RK3_S3 : BASE_P0);
+                const bool has_p0 = SB < 0 ? A.p0 >= 0 : (SB == SB_S2 || SB == SB_S3 || SB == SB_P0);
+                const bool has_out2 = SB < 0 ? P.out2 != nullptr : SB == SB_IN_OUT2;
                 T x = qc;
-                if (A.p0 >= 0) {
-                    const T pn = auxz[A.p0 * G::TILE + st];
-                    if (P.base == BASE_RK3_S2) x = T(fma(0.75, double(pn), 0.25 * double(qc)));       // timestepping.jl:183
-                    else if (P.base == BASE_RK3_S3) x = div3(T(pn + T(2) * qc));                       // timestepping.jl:194
+                if (has_p0) {
+                    const T pn = auxz[(SB < 0 ? A.p0 : SP0) * G::TILE + st];
+                    if (base == BASE_RK3_S2) x = T(fma(0.75, double(pn), 0.25 * double(qc)));       // timestepping.jl:183
+                    else if (base == BASE_RK3_S3) x = div3(T(pn + T(2) * qc));                       // timestepping.jl:194
                     else x = pn;                                                                       // RK2 S2 (corr)
                 }
                 T x2 = qc;
@@ -626,7 +634,7 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                         H = q < eps ? b * 0.0 : b * (fma(tr, q, -quad) * fast_rcp<2>(q));
                     }
                     x = T(fma(-P.c, H, double(x)));
-                    if (P.out2) x2 = T(fma(-P.c2, H, double(x2)));
+                    if (has_out2) x2 = T(fma(-P.c2, H, double(x2)));
                 };
                 if (NTS > 0) {
                     one_term(P.terms[0], 0, std::integral_constant<int, 0>{});
@@ -637,7 +645,7 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                 }
                 const long lin = lin_k[k];
                 P.out[lin] = x;
-                if (P.out2) P.out2[lin] = x2;
+                if (has_out2) P.out2[lin] = x2;
             }
         }
         if (NDIM == 3) {
@@ -703,11 +711,11 @@ bool encode_map3(CUtensorMap* m, const void* base, long n0, long n1, long nplane
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL = false, int TK = -1>
+template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL = false, int TK = -1, int SB = -1>
 cudaError_t launch_tiled(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
     constexpr int TX = LSM_TX, TY = LSM_TY, NY = LSM_NY;
     using G = TileGeom<T, NDIM, TX, TY, NY>;
-    auto kern = stage_tiled_kernel<T, NDIM, MASK, NTS, COEFK, REMAP, FCFL, TX, TY, NY, LSM_MINB, TK>;
+    auto kern = stage_tiled_kernel<T, NDIM, MASK, NTS, COEFK, REMAP, FCFL, TX, TY, NY, LSM_MINB, TK, SB>;
     const size_t smem = G::smem_bytes(A.n);
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
@@ -739,6 +747,26 @@ cudaError_t launch_tiled(const StageParams<T>& P, const AuxList& A, cudaStream_t
     return cudaGetLastError();
 }
 
+// Static-signature kernels also fix the RK base mode at compile time (5 legal combinations of BASE_* and out2); anything
+// unexpected (phi^n staged in another aux slot) takes the runtime-base instantiation.
+template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL, int TK>
+cudaError_t launch_static(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
+    constexpr int SP0 = TK >= 0 ? sig_first(TK, COEFK, NTS, NDIM) : (COEFK == COEF_FIELD ? NDIM : 0);
+    const bool p0_ok = A.p0 < 0 || A.p0 == SP0;
+    if (p0_ok) {
+        if (P.base == BASE_IN && !P.p0) {
+            if (!P.out2) return launch_tiled<T, NDIM, MASK, NTS, COEFK, REMAP, FCFL, TK, SB_IN>(P, A, s);
+            if (!FCFL) return launch_tiled<T, NDIM, MASK, NTS, COEFK, REMAP, false, TK, SB_IN_OUT2>(P, A, s);
+        }
+        if (P.base == BASE_RK3_S2 && P.p0 && !P.out2 && !FCFL) return launch_tiled<T, NDIM, MASK, NTS, COEFK, REMAP, false, TK, SB_S2>(P, A, s);
+        if (P.base == BASE_RK3_S3 && P.p0 && !P.out2) return launch_tiled<T, NDIM, MASK, NTS, COEFK, REMAP, FCFL, TK, SB_S3>(P, A, s);
+        if (P.base == BASE_P0 && P.p0 && !P.out2) return launch_tiled<T, NDIM, MASK, NTS, COEFK, REMAP, FCFL, TK, SB_P0>(P, A, s);
+    }
+    // (cannot happen with the aux list launch_stage_tiled builds; the all-terms kernel handles anything, and a requested fused CFL
+    //  that is not delivered makes the host fall back to the separate reduction pass)
+    return launch_tiled<T, NDIM, M_ALL, 0, -1, REMAP>(P, A, s);
+}
+
 template <class T, int NDIM, bool REMAP>
 cudaError_t launch_by_mask(int mask, const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
     if constexpr (REMAP) {
@@ -747,14 +775,14 @@ cudaError_t launch_by_mask(int mask, const StageParams<T>& P, const AuxList& A, 
                 if (P.nterms == 1) {
                     const TermDev& t0 = P.terms[0];
                     if (t0.coef_kind == COEF_FIELD && A.first[0] == 0) {
-                        if (NDIM == 3 && P.cfl_out) return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_FIELD, REMAP, true>(P, A, s);
-                        return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_FIELD, REMAP>(P, A, s);
+                        if (NDIM == 3 && P.cfl_out) return launch_static<T, NDIM, M_ADV_WENO, 1, COEF_FIELD, REMAP, true, -1>(P, A, s);
+                        return launch_static<T, NDIM, M_ADV_WENO, 1, COEF_FIELD, REMAP, false, -1>(P, A, s);
                     }
                     if (t0.coef_kind == COEF_SEPARABLE) {
-                        if (NDIM == 3 && P.cfl_out) return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_SEPARABLE, REMAP, true>(P, A, s);
-                        return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_SEPARABLE, REMAP>(P, A, s);
+                        if (NDIM == 3 && P.cfl_out) return launch_static<T, NDIM, M_ADV_WENO, 1, COEF_SEPARABLE, REMAP, true, -1>(P, A, s);
+                        return launch_static<T, NDIM, M_ADV_WENO, 1, COEF_SEPARABLE, REMAP, false, -1>(P, A, s);
                     }
-                    if (t0.coef_kind == COEF_CONST) return launch_tiled<T, NDIM, M_ADV_WENO, 1, COEF_CONST, REMAP>(P, A, s);
+                    if (t0.coef_kind == COEF_CONST) return launch_static<T, NDIM, M_ADV_WENO, 1, COEF_CONST, REMAP, false, -1>(P, A, s);
                 }
                 break;
             // static signatures (term kinds, coefficient kinds and aux-tile slots known at compile time) for the BASELINE
@@ -762,8 +790,8 @@ cudaError_t launch_by_mask(int mask, const StageParams<T>& P, const AuxList& A, 
             case M_EIK:
                 if (P.nterms == 1) {
                     const TermDev& t0 = P.terms[0];
-                    if (t0.coef_kind == COEF_FIELD && A.first[0] == 0) return launch_tiled<T, NDIM, M_EIK, 1, COEF_FIELD, REMAP, false, SK_EIK>(P, A, s);
-                    if (t0.coef_kind == COEF_NONE) return launch_tiled<T, NDIM, M_EIK, 1, COEF_NONE, REMAP, false, SK_EIK>(P, A, s);
+                    if (t0.coef_kind == COEF_FIELD && A.first[0] == 0) return launch_static<T, NDIM, M_EIK, 1, COEF_FIELD, REMAP, false, SK_EIK>(P, A, s);
+                    if (t0.coef_kind == COEF_NONE) return launch_static<T, NDIM, M_EIK, 1, COEF_NONE, REMAP, false, SK_EIK>(P, A, s);
                     return launch_tiled<T, NDIM, M_EIK, 1, -1, REMAP>(P, A, s);
                 }
                 break;
@@ -771,7 +799,7 @@ cudaError_t launch_by_mask(int mask, const StageParams<T>& P, const AuxList& A, 
                 if (P.nterms == 2) {
                     const TermDev &t0 = P.terms[0], &t1 = P.terms[1];
                     if (t0.kind == TERM_NORMAL && t0.coef_kind == COEF_FIELD && A.first[0] == 0 && t1.coef_kind == COEF_FIELD && A.first[1] == 1)
-                        return launch_tiled<T, NDIM, M_NORMAL | M_ADV_WENO, 2, COEF_FIELD | (COEF_FIELD << 2), REMAP, false, SK_NORMAL | (SK_ADV_WENO << 3)>(P, A, s);
+                        return launch_static<T, NDIM, M_NORMAL | M_ADV_WENO, 2, COEF_FIELD | (COEF_FIELD << 2), REMAP, false, SK_NORMAL | (SK_ADV_WENO << 3)>(P, A, s);
                     return launch_tiled<T, NDIM, M_NORMAL | M_ADV_WENO, 2, -1, REMAP>(P, A, s);
                 }
                 break;
@@ -779,7 +807,7 @@ cudaError_t launch_by_mask(int mask, const StageParams<T>& P, const AuxList& A, 
                 if (P.nterms == 2) {
                     const TermDev &t0 = P.terms[0], &t1 = P.terms[1];
                     if (t0.kind == TERM_ADVECTION && t0.coef_kind == COEF_FIELD && A.first[0] == 0 && t1.coef_kind == COEF_CONST)
-                        return launch_tiled<T, NDIM, M_ADV_WENO | M_CURV, 2, COEF_FIELD | (COEF_CONST << 2), REMAP, false, SK_ADV_WENO | (SK_CURV << 3)>(P, A, s);
+                        return launch_static<T, NDIM, M_ADV_WENO | M_CURV, 2, COEF_FIELD | (COEF_CONST << 2), REMAP, false, SK_ADV_WENO | (SK_CURV << 3)>(P, A, s);
                     return launch_tiled<T, NDIM, M_ADV_WENO | M_CURV, 2, -1, REMAP>(P, A, s);
                 }
                 break;
@@ -840,9 +868,15 @@ cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, 
     return remap ? launch_by_mask<T, 2, true>(mask, P, A, s) : launch_by_mask<T, 2, false>(mask, P, A, s);
 }
 
+// The Makefile compiles this file twice (-DLSM_TILED_F32 / -DLSM_TILED_F64) so that the two halves of the ~180 kernel
+// instantiations build in parallel; without either macro both are instantiated here.
+#if !defined(LSM_TILED_F64)
 template bool stage_tiled_supported<float>(int, const StageParams<float>&);
-template bool stage_tiled_supported<double>(int, const StageParams<double>&);
 template cudaError_t launch_stage_tiled<float>(int, const StageParams<float>&, int, cudaStream_t);
+#endif
+#if !defined(LSM_TILED_F32)
+template bool stage_tiled_supported<double>(int, const StageParams<double>&);
 template cudaError_t launch_stage_tiled<double>(int, const StageParams<double>&, int, cudaStream_t);
+#endif
 
 }  // namespace lsm
