@@ -30,3 +30,19 @@ run_case("C4_48", g, f4, (EikonalReinitializationTerm(MeshField(f4, g)),), Neuma
 # C5: NormalMotion(v = 0.2 field) + Advection(u = (-y, x, 0) field), 48^3, Neumann
 v = MeshField(x -> 0.2, g); u3 = MeshField(x -> SVector(-x[2], x[1], 0.0), g)
 run_case("C5_48", g, x -> norm(x .- SVector(0.3, 0.0, 0.0)) - 0.4, (NormalMotionTerm(v), AdvectionTerm(u3)), NeumannBC(), 100)
+
+# ---- "next" rows (SURVEY.md §8f): scalars and arrays for volume / perimeter, set operations, velocity extension ----
+function dump(name, A)
+    open(io -> write(io, A), joinpath(ARGS[1], "$name.f64"), "w")
+end
+g2 = CartesianGrid((-1.0, -1.0), (1.0, 1.0), (81, 61))
+a = MeshField(x -> hypot(x[1] - 0.2, x[2]) - 0.5, g2)
+b = MeshField(x -> max(abs(x[1] + 0.1), abs(x[2])) - 0.4, g2)
+println("volume(a) = ", repr(LSM.volume(a)), "  perimeter(a) = ", repr(LSM.perimeter(a)))
+dump("csg_union", values(union(a, b))); dump("csg_intersect", values(intersect(a, b)))
+dump("csg_setdiff", values(setdiff(a, b))); dump("csg_complement", values(LSM.complement(a)))
+# extend_along_normals! on the grid of test/test-velocityextension.jl (default band mask, 12 iterations)
+ϕe = MeshField(x -> (hypot(x[1], x[2]) - 0.5) * (1 + 0.2 * x[1]), g2)
+F = [sin(3 * x) + y^2 for x in LSM.grid1d(g2, 1), y in LSM.grid1d(g2, 2)]
+extend_along_normals!(F, ϕe; nb_iters = 12)
+dump("extend_81x61", F)
