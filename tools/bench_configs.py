@@ -101,7 +101,7 @@ def main():
         ("C5 3-D normal motion + advection 512^3 f64 (1-GPU slice of the 1024^3 config)", lambda: H.c5_normal_advection(512, f64), m.RK3(), 160.0),
     ]
     for name, mk, integ, balg in cfgs:
-        if (a.only and not name.startswith(a.only)) or (a.skip and name.startswith(a.skip)):
+        if (a.only and not any(name.startswith(o) for o in a.only.split(","))) or (a.skip and name.startswith(a.skip)):
             continue
         run(name, mk(), integ, balg, a.steps if "128^2" not in name else 10 * a.steps, a.warmup, a.reps)
 
