@@ -114,3 +114,38 @@ def test_equation_construction_errors(m):
     assert eq.state is not phi and np.array_equal(eq.state.peek(), phi.peek())     # ic is copied
     with pytest.raises(m.TimeError):
         m.integrate(eq, -1.0)                                                      # levelsetequation.jl:196
+
+
+def test_next_row_argument_checks_need_no_gpu(m):
+    """The argument checks of the "next" rows (velocityextension.jl:25-37, test-velocityextension.jl:87-101; set operations on
+    equal-size real-valued fields) fire on the host, before any device work."""
+    g = m.CartesianGrid((-1, -1), (1, 1), (41, 41))
+    phi = m.MeshField(lambda x: x[0] + x[1], g)
+    F = m.MeshField(np.zeros((41, 41)), g)
+    with pytest.raises(ValueError):
+        m.extend_along_normals(F, phi, nb_iters=-1)
+    with pytest.raises(ValueError):
+        m.extend_along_normals(F, phi, cfl=0.0)
+    with pytest.raises(ValueError):
+        m.extend_along_normals(m.MeshField(np.zeros((2, 2)), m.CartesianGrid((-1, -1), (1, 1), (2, 2))), phi)
+    with pytest.raises(ValueError):
+        m.extend_along_normals(F, phi, frozen=np.zeros((40, 41), dtype=bool))
+    with pytest.raises(ValueError):
+        m.extend_along_normals(F, phi, frozen=np.zeros((41, 41), dtype=np.int32))      # mask must contain Bool values
+    with pytest.raises(ValueError):
+        m.union_(phi, m.MeshField(np.zeros((4, 4)), m.CartesianGrid((-1, -1), (1, 1), (4, 4))))
+    u = m.MeshField(lambda x: (-x[1], x[0]), g)
+    with pytest.raises(ValueError):
+        m.complement_(u)                                                                # check_real_valued (levelsetops.jl:254)
+
+
+def test_fails_loudly_without_the_extension(tmp_path):
+    """The product has no CPU fallback: with the shared library missing, the first call raises ImportError (checked in a
+    fresh interpreter so that this process's loaded library is untouched)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import lsm_b200 as m\n"
+            "try:\n    m._lib.lib()\nexcept ImportError as e:\n    print('LOUD', 'no CPU fallback' in str(e))\n" % ROOT)
+    env = dict(os.environ, LSM_B200_SO=str(tmp_path / "does_not_exist.so"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert "LOUD True" in out.stdout, out.stdout + out.stderr
