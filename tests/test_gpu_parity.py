@@ -556,20 +556,24 @@ def test_graph_replay_is_invisible(m, O):
         assert np.abs(res[0][0] - fo.vals).max() < 1e-3
 
 
-def test_counters_and_launch_accounting(m):
+@pytest.mark.parametrize("integ", ["RK3", "RK2", "FE"])
+def test_counters_and_launch_accounting(m, integ):
+    """Launch accounting and the fused next-step CFL (exact, so states are bit-identical with the option off) for all three
+    integrators: the last stage of each runs its own fused-CFL instantiation (RK3 S3, RK2 corrector, ForwardEuler)."""
     ctx = m.default_context()
     case = H.c3_enright(32)
+    mk, nst = {"RK3": (m.RK3, 3), "RK2": (m.RK2, 2), "FE": (m.ForwardEuler, 1)}[integ]
     results = []
     for fuse in (0, 1):
         ctx.set_option(m._lib.OPT_FUSE_CFL, fuse)
         phi = case.engine_field(m)
-        eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=m.RK3())
+        eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=mk())
         eq.state.device()
         eq.terms[0].velocity.base.device()            # upload the coefficient (one AoS->SoA kernel) before counting
         ctx.reset_counters()
         m.integrate(eq, 0.02)
         c = ctx.counters()
-        assert c["stage_launches"] == 3 * eq.steps_taken
+        assert c["stage_launches"] == nst * eq.steps_taken
         # cos(pi t/T) changes every step: one CFL reduction per step, unless the last RK stage of the previous step
         # already produced it (fused CFL) — then only the very first step needs a separate pass
         assert c["cfl_passes"] == (1 if fuse else eq.steps_taken)
