@@ -151,13 +151,21 @@ def cpu_leg(steps, warmup, threads):
     return nodes * steps / sec, sec / steps
 
 
+def host_threads():
+    """Threads the CPU legs use: every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which would
+    otherwise silently serialise the reference arm under N > 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is 100 % Julia
     and Julia is not in this image, so this is the oracle port (kind "port") with all host threads."""
     if rank != 0:
         return
-    import oracle as O
-    threads = O.max_threads()
+    threads = host_threads()
     v, sps = cpu_leg(args.steps, max(args.warmup, 1), threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -340,8 +348,7 @@ def main():
         "e2e": e2e,
     }
     if G == 1 and not args.no_cpu:
-        import oracle as O
-        thr = O.max_threads()
+        thr = host_threads()
         v_all, _ = cpu_leg(3, 1, thr)
         v_one, _ = cpu_leg(1, 0, 1)
         line["cpu_baseline"] = {"value": v_all, "unit": UNIT, "cores": thr, "kind": "port",
