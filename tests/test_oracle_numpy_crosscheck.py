@@ -149,29 +149,7 @@ def _eikonal_frozen(phi, S0, h):
 
 
 def _curvature_term(phi, b, h):
-    G = _Periodic(phi, h)
-    N = phi.ndim
-    g = [G.D0(d) for d in range(N)]
-    nrmsq = g[0] * g[0]
-    for d in range(1, N):
-        nrmsq = nrmsq + g[d] * g[d]
-    Hm = [[None] * N for _ in range(N)]
-    for i in range(N):
-        Hm[i][i] = (G.at(*G.e(i)) - 2 * G.at() + G.at(*G.e(i, -1))) / h[i] ** 2
-        for j in range(i + 1, N):                     # upper triangle: D2(phi, I, (i, j))
-            Hm[i][j] = Hm[j][i] = (G.D0(j, G.e(i)) - G.D0(j, G.e(i, -1))) / (2 * h[i])
-    tr = Hm[0][0]
-    for d in range(1, N):
-        tr = tr + Hm[d][d]
-    quad = None
-    for j in range(N):                                # (g' H) g
-        col = g[0] * Hm[0][j]
-        for i in range(1, N):
-            col = col + g[i] * Hm[i][j]
-        quad = col * g[j] if j == 0 else quad + col * g[j]
-    with np.errstate(divide="ignore", invalid="ignore"):
-        kappa = np.where(nrmsq < np.finfo(np.float64).eps, 0.0, (tr * nrmsq - quad) / nrmsq ** 1.5)
-    return b * kappa * np.sqrt(nrmsq)
+    return _curvature_term_padded(_Periodic(phi, h), b, h)
 
 
 @pytest.mark.parametrize("n", [(40, 36), (18, 16, 14)])
@@ -204,3 +182,97 @@ def test_numpy_godunov_and_curvature_agree_with_oracle(O, n):
         O.advance(f, O.FE, [term], 0.0, 0.5 * min(h))
         phi = phi - (0.5 * min(h)) * _eikonal_frozen(phi, S0, h)
     assert np.abs(phi - f.vals).max() <= 2e-15
+
+
+# ---- ghost cells of ExtrapolationBC{P} / SymmetryBC with corner composition (boundaryconditions.jl:90-97,132-153;
+# ---- meshfield.jl:248-260): padding axis by axis, lowest dimension first, equals the reference's dim N -> 1 recursion ----
+def _w(j, k, P):
+    w = 1.0
+    for mm in range(P + 1):
+        if mm != j:
+            w *= (-k - mm) / (j - mm)
+    return w
+
+
+def _pad_bc(a, axis, kind, P=0, g=3):
+    n = a.shape[axis]
+    a = np.moveaxis(a, axis, 0)
+    lo, hi = [], []
+    for k in range(g, 0, -1):                         # ghosts at distance k below node 1 (stored from far to near)
+        if kind == "sym":
+            lo.append(a[k])
+        else:
+            acc = np.zeros_like(a[0])
+            for j in range(P + 1):
+                acc = acc + _w(j, k, P) * a[j]
+            lo.append(acc)
+    for k in range(1, g + 1):
+        if kind == "sym":
+            hi.append(a[n - 1 - k])
+        else:
+            acc = np.zeros_like(a[0])
+            for j in range(P + 1):
+                acc = acc + _w(j, k, P) * a[n - 1 - j]
+            hi.append(acc)
+    return np.moveaxis(np.concatenate([np.stack(lo), a, np.stack(hi)], axis=0), 0, axis)
+
+
+class _Padded(_Periodic):
+    def __init__(self, phi, h, bcs):                  # bcs[d] = (kind, P)
+        self.n, self.h, self.N = phi.shape, h, phi.ndim
+        P = phi
+        for d in range(phi.ndim):                     # dimension 1 first: the recursion resolves dim N outermost, dim 1 innermost
+            P = _pad_bc(P, d, *bcs[d])
+        self.P = P
+
+
+@pytest.mark.parametrize("n", [(30, 26), (14, 13, 12)])
+def test_numpy_ghost_composition_agrees_with_oracle(O, n):
+    """Every ghost the stencils can touch (3 deep, corners and edges included) for Neumann, linear / quadratic extrapolation and
+    symmetry, then one curvature + upwind step that reads them."""
+    N = len(n)
+    rng = np.random.default_rng(5)
+    phi0 = np.asfortranarray(rng.standard_normal(n))
+    kinds = [("extrap", 0), ("extrap", 2), ("sym", 0)][:N] if N == 3 else [("extrap", 1), ("sym", 0)]
+    obc = [O.EXTRAP(p) if k == "extrap" else O.SYMMETRY for k, p in kinds]
+    f = O.Field(phi0.copy(order="F"), (-1.0,) * N, (1.0,) * N, bc=obc)
+    h = [f.meshsize(d + 1) for d in range(N)]
+    G = _Padded(phi0, h, kinds)
+    worst = 0.0
+    import itertools
+    for off in itertools.product(*[range(-3, m + 3) for m in n]):
+        if all(0 <= o < m for o, m in zip(off, n)):
+            continue
+        if sum(1 for o, m in zip(off, n) if not 0 <= o < m) < 2 and rng.random() > 0.1:
+            continue                                   # all corners / edges, a sample of the faces
+        ref = f[tuple(o + 1 for o in off)]
+        worst = max(worst, abs(ref - G.P[tuple(o + 3 for o in off)]))
+    assert worst <= 1e-12, worst
+    phi = phi0 - 1e-4 * _curvature_term_padded(G, -0.05, h)
+    O.advance(f, O.FE, [O.curvature(-0.05)], 0.0, 1e-4)
+    assert np.abs(phi - f.vals).max() <= 1e-12
+
+
+def _curvature_term_padded(G, b, h):
+    N = G.N
+    g = [G.D0(d) for d in range(N)]
+    nrmsq = g[0] * g[0]
+    for d in range(1, N):
+        nrmsq = nrmsq + g[d] * g[d]
+    Hm = [[None] * N for _ in range(N)]
+    for i in range(N):
+        Hm[i][i] = (G.at(*G.e(i)) - 2 * G.at() + G.at(*G.e(i, -1))) / h[i] ** 2
+        for j in range(i + 1, N):
+            Hm[i][j] = Hm[j][i] = (G.D0(j, G.e(i)) - G.D0(j, G.e(i, -1))) / (2 * h[i])
+    tr = Hm[0][0]
+    for d in range(1, N):
+        tr = tr + Hm[d][d]
+    quad = None
+    for j in range(N):
+        col = g[0] * Hm[0][j]
+        for i in range(1, N):
+            col = col + g[i] * Hm[i][j]
+        quad = col * g[j] if j == 0 else quad + col * g[j]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        kappa = np.where(nrmsq < np.finfo(np.float64).eps, 0.0, (tr * nrmsq - quad) / nrmsq ** 1.5)
+    return b * kappa * np.sqrt(nrmsq)
