@@ -276,3 +276,47 @@ def _curvature_term_padded(G, b, h):
     with np.errstate(divide="ignore", invalid="ignore"):
         kappa = np.where(nrmsq < np.finfo(np.float64).eps, 0.0, (tr * nrmsq - quad) / nrmsq ** 1.5)
     return b * kappa * np.sqrt(nrmsq)
+
+
+# ---- Float32 fields: Julia's promotion rules (the reference never tests them; SURVEY.md §8a "precision notes") ----------
+def _advection_f32(phi, u, h):
+    """phi, u Float32.  The first difference is Float32 (V - V), the division by the Float64 meshsize promotes, everything
+    after is Float64 (all literals are Float64); u_d * weno is Float32 * Float64 -> Float64."""
+    H = None
+    for d in range(phi.ndim):
+        n = phi.shape[d]
+        P = _pad_periodic(phi, d)
+        at = lambda k: np.take(P, np.arange(3 + k, 3 + k + n), axis=d)
+        Dm = lambda k: (at(k) - at(k - 1)).astype(np.float64) / h[d]
+        Dp = lambda k: (at(k + 1) - at(k)).astype(np.float64) / h[d]
+        wm = _weno5(Dm(-2), Dm(-1), Dm(0), Dm(1), Dm(2))
+        wp = _weno5(Dp(2), Dp(1), Dp(0), Dp(-1), Dp(-2))
+        term = u[d].astype(np.float64) * np.where(u[d] > 0, wm, wp)
+        H = term if d == 0 else H + term
+    return H
+
+
+def _rk3_f32(phi, u, h, dt):
+    f32, f64 = np.float32, np.float64
+    b1 = (phi.astype(f64) - dt * _advection_f32(phi, u, h)).astype(f32)                  # buf1[I] -= dt * H   (store rounds)
+    b2 = (0.75 * phi.astype(f64) + 0.25 * b1.astype(f64)).astype(f32)                    # Float64 literals promote
+    b2 = (b2.astype(f64) - 0.25 * dt * _advection_f32(b1, u, h)).astype(f32)
+    b3 = ((phi + f32(2) * b2) / f32(3)).astype(f32)                                      # (phi + 2 buf2) / 3 stays in Float32
+    return (b3.astype(f64) - (2 / 3) * dt * _advection_f32(b2, u, h)).astype(f32)
+
+
+def test_numpy_float32_promotion_agrees_with_oracle(O):
+    n = (40, 34)
+    f = O.Field(np.zeros(n, dtype=np.float32, order="F"), (-1.0, -1.0), (1.0, 1.0), bc=O.PERIODIC)
+    X = f.nodes()
+    f.vals[...] = np.broadcast_to(np.hypot(X[0] - 0.3, X[1]) - 0.4, n).astype(np.float32)
+    u = np.asfortranarray(np.stack([np.broadcast_to(-X[1], n), np.broadcast_to(X[0], n)]).astype(np.float32))
+    h = [f.meshsize(1), f.meshsize(2)]
+    terms = [O.advection(u)]
+    dt = 0.5 * O.compute_cfl(f, terms, 0.0)
+    phi = f.vals.copy()
+    for _ in range(5):
+        O.advance(f, O.RK3, terms, 0.0, dt)
+        phi = _rk3_f32(phi, u, h, dt)
+    assert phi.dtype == np.float32 and f.vals.dtype == np.float32
+    assert np.array_equal(phi, f.vals)          # same IEEE operations in the same order: bit-identical
