@@ -320,3 +320,49 @@ def test_numpy_float32_promotion_agrees_with_oracle(O):
         phi = _rk3_f32(phi, u, h, dt)
     assert phi.dtype == np.float32 and f.vals.dtype == np.float32
     assert np.array_equal(phi, f.vals)          # same IEEE operations in the same order: bit-identical
+
+
+# ---- extend_along_normals! (velocityextension.jl:20-116), whole-array restatement -------------------------------------
+def _extend(F, phi, h, bcs, nb_iters, cfl=0.45, frozen=None, band=1.5, min_norm=1e-14):
+    N = phi.ndim
+    D = min(h)
+    tau = cfl * D
+    Gp = _Padded(phi, h, bcs)
+    frozen = np.abs(phi) <= band * D if frozen is None else frozen
+    g = [Gp.D0(d) for d in range(N)]
+    n2 = g[0] ** 2
+    for d in range(1, N):
+        n2 = n2 + g[d] ** 2
+    ok = n2 > min_norm ** 2
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / np.sqrt(n2)
+        S = phi / np.sqrt(phi ** 2 + D ** 2)
+        a = [np.where(ok, (S * g[d]) * inv, 0.0) for d in range(N)]
+    F = F.copy()
+    for _ in range(nb_iters):
+        G = _Padded(F, h, bcs)
+        adv = np.zeros_like(F)
+        for d in range(N):
+            dm = (G.at() - G.at(*G.e(d, -1))) / h[d]
+            dp = (G.at(*G.e(d)) - G.at()) / h[d]
+            adv = adv + a[d] * np.where(a[d] > 0, dm, dp)
+        F = np.where(frozen, F, F - tau * adv)
+    return F
+
+
+@pytest.mark.parametrize("n,kinds", [((41, 37), [("extrap", 1), ("extrap", 1)]), ((41, 37), [("extrap", 0), ("sym", 0)]),
+                                     ((18, 17, 16), [("extrap", 1)] * 3)])
+def test_numpy_velocity_extension_agrees_with_oracle(O, n, kinds):
+    N = len(n)
+    default_bc = all(k == ("extrap", 1) for k in kinds)          # a field without BCs gets LinearExtrapolationBC (:38-43)
+    obc = None if default_bc else [O.EXTRAP(p) if k == "extrap" else O.SYMMETRY for k, p in kinds]
+    f = O.Field(np.zeros(n, order="F"), (-1.0,) * N, (1.0,) * N, bc=obc)
+    X = f.nodes()
+    r = np.sqrt(sum(x * x for x in X))
+    f.vals[...] = np.broadcast_to((r - 0.5) * (1 + 0.2 * X[0]), n)
+    F0 = np.asfortranarray(np.broadcast_to(np.sin(3 * X[0]) + X[1] ** 2, n).copy())
+    h = [f.meshsize(d + 1) for d in range(N)]
+    for frozen in (None, np.asfortranarray(np.abs(f.vals) < 0.07)):
+        ref = O.extend_along_normals(F0.copy(order="F"), f, nb_iters=9, frozen=frozen)
+        mine = _extend(F0, f.vals, h, kinds, 9, frozen=frozen)
+        assert np.abs(ref - mine).max() <= 1e-14, np.abs(ref - mine).max()
