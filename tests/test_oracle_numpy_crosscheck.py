@@ -366,3 +366,31 @@ def test_numpy_velocity_extension_agrees_with_oracle(O, n, kinds):
         ref = O.extend_along_normals(F0.copy(order="F"), f, nb_iters=9, frozen=frozen)
         mine = _extend(F0, f.vals, h, kinds, 9, frozen=frozen)
         assert np.abs(ref - mine).max() <= 1e-14, np.abs(ref - mine).max()
+
+
+# ---- RK2 (Heun, timestepping.jl:143-164) and a two-term equation with the per-term sequential subtraction ---------------
+def test_numpy_rk2_two_terms_agrees_with_oracle(O):
+    n = (36, 30)
+    f = O.Field(np.zeros(n, order="F"), (-1.0, -1.0), (1.0, 1.0), bc=O.PERIODIC)
+    X = f.nodes()
+    f.vals[...] = np.broadcast_to((np.hypot(X[0] - 0.1, X[1]) - 0.5) * (1 + 0.3 * np.sin(3 * X[0])), n)
+    h = [f.meshsize(1), f.meshsize(2)]
+    u = np.asfortranarray(np.stack([np.broadcast_to(-X[1], n), np.broadcast_to(X[0], n)]))
+    v = np.asfortranarray(np.broadcast_to(0.2 + 0.3 * np.cos(2 * X[1]), n).copy())
+    terms = [O.normal_motion(v), O.advection(u)]
+    L = [lambda p: _normal_motion(p, v, h), lambda p: _advection(p, u, h)]
+    dt = 0.5 * O.compute_cfl(f, terms, 0.0)
+    # compute_cfl: minimum over terms of the per-term node minimum (levelsetterms.jl:22-38)
+    assert dt == 0.5 * min(1 / np.max(np.abs(v) / h[0] + np.abs(v) / h[1]), 1 / np.max(np.abs(u[0]) / h[0] + np.abs(u[1]) / h[1]))
+    phi = f.vals.copy()
+    for _ in range(4):
+        O.advance(f, O.RK2, terms, 0.0, dt)
+        pred, corr = phi.copy(), phi.copy()
+        for Lk in L:                                   # pred -= dt*v ; corr -= 0.5*dt*v, term after term
+            val = Lk(phi)
+            pred = pred - dt * val
+            corr = corr - 0.5 * dt * val
+        for Lk in L:
+            corr = corr - 0.5 * dt * Lk(pred)
+        phi = corr
+    assert np.abs(phi - f.vals).max() <= 2e-15, np.abs(phi - f.vals).max()
