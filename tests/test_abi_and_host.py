@@ -27,6 +27,13 @@ def test_header_symbols_all_exported(m):
     assert lib.lsm_abi_version() == 1
 
 
+def test_integration_doc_covers_every_entry_point():
+    hdr = open(os.path.join(ROOT, "include", "lsm_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [f for f in set(re.findall(r"\b(lsm_[a-z0-9_]+)\s*\(", hdr)) if f not in doc]
+    assert not missing, f"INTEGRATION.md does not mention {missing}"
+
+
 def test_header_cites_reference(m):
     hdr = open(os.path.join(ROOT, "include", "lsm_b200.h")).read()
     for cite in ("timestepping.jl:101-122", "levelsetterms.jl:22-38", "meshfield.jl:213-260", "boundaryconditions.jl:166-188"):
