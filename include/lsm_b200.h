@@ -91,11 +91,12 @@ typedef struct {
     double  last_stage_ms;    /* CUDA-event time of the last timed stage (see LSM_OPT_TIME_STAGES) */
     double  sum_stage_ms;     /* accumulated over timed stages since lsm_reset_counters */
     int64_t timed_stages;
+    int64_t pair_launches;    /* stage launches that took the x-pair kernel (3-D single-term WENO5 advection)  */
 } lsm_counters;
 
 /* options for lsm_set_option */
 enum {
-    LSM_OPT_KERNEL = 0,       /* 0 auto (tiled where available), 1 force generic strict kernel, 2 force tiled */
+    LSM_OPT_KERNEL = 0,       /* 0 auto (x-pair / tiled where available), 1 force generic strict kernel, 2 force tiled / x-pair, 3 tiled without the x-pair kernel */
     LSM_OPT_TIME_STAGES = 1,  /* 1: bracket every stage launch with CUDA events, resolved at the next sync  */
     LSM_OPT_CFL_CACHE = 2,    /* 1 (default): reuse the CFL reduction while coefficient data/scale unchanged  */
     LSM_OPT_OVERLAP = 3,      /* 1 (default): overlap halo exchange with interior compute (multi-rank)        */

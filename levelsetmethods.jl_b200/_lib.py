@@ -38,7 +38,8 @@ class lsm_term(C.Structure):
 class lsm_counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("stage_launches", C.c_int64), ("cfl_passes", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("halo_bytes_sent", C.c_int64),
-                ("last_stage_ms", C.c_double), ("sum_stage_ms", C.c_double), ("timed_stages", C.c_int64)]
+                ("last_stage_ms", C.c_double), ("sum_stage_ms", C.c_double), ("timed_stages", C.c_int64),
+                ("pair_launches", C.c_int64)]
 
 
 class LSMError(RuntimeError):

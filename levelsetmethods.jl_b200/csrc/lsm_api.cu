@@ -303,11 +303,12 @@ int32_t launch_stage_range(lsm_ctx* c, int ndim, StageParams<T>& P, int r0, int 
     if (r1 <= r0) return LSM_OK;
     P.r0 = r0; P.r1 = r1;
     cudaError_t e = cudaErrorNotSupported;
-    if (c->opt_kernel != 1 && stage_tiled_supported<T>(ndim, P)) e = launch_stage_tiled<T>(ndim, P, c->sm_count, st);
+    int used_pair = 0;
+    if (c->opt_kernel != 1 && stage_tiled_supported<T>(ndim, P)) e = launch_stage_tiled<T>(ndim, P, c->sm_count, st, c->opt_kernel != 3, &used_pair);
     else if (c->opt_kernel == 2) return fail(LSM_ERR_UNSUPPORTED, "tiled kernel forced but this configuration is not covered");
     if (e == cudaErrorNotSupported) e = launch_stage_generic<T>(ndim, P, st);
     if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "stage kernel launch failed: %s", cudaGetErrorString(e));
-    c->cnt.kernel_launches += 1; c->cnt.stage_launches += 1;
+    c->cnt.kernel_launches += 1; c->cnt.stage_launches += 1; c->cnt.pair_launches += used_pair;
     return LSM_OK;
 }
 
@@ -610,7 +611,7 @@ int32_t lsm_sync(lsm_ctx* c) {
 int32_t lsm_set_option(lsm_ctx* c, int32_t option, int32_t value) {
     if (!c) return fail(LSM_ERR_ARG, "null context");
     switch (option) {
-        case LSM_OPT_KERNEL: if (value < 0 || value > 2) return fail(LSM_ERR_ARG, "LSM_OPT_KERNEL takes 0, 1 or 2"); c->opt_kernel = value; break;
+        case LSM_OPT_KERNEL: if (value < 0 || value > 3) return fail(LSM_ERR_ARG, "LSM_OPT_KERNEL takes 0, 1, 2 or 3"); c->opt_kernel = value; break;
         case LSM_OPT_TIME_STAGES: c->opt_time = value != 0; break;
         case LSM_OPT_CFL_CACHE: c->opt_cfl_cache = value != 0; c->cfl_cache.clear(); break;
         case LSM_OPT_OVERLAP: c->opt_overlap = value != 0; break;

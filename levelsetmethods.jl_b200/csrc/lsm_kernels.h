@@ -22,9 +22,26 @@ template <class T> cudaError_t launch_signed_normals(int ndim, const View<T>& v,
 cudaError_t launch_csg(int f64, void* dst, const void* src, long n, int op, cudaStream_t s);
 cudaError_t launch_max_abs_diff(int f64, const void* a, const void* b, long n, unsigned long long* out, cudaStream_t s);
 
+// The five Float64 constants of the WENO5 evaluation that do not fit an instruction immediate travel in the kernel parameters
+// (constant bank): as literals the compiler re-materialises them with 10 UMOV per node, from the constant bank it takes 3 uniform loads.
+struct WenoK { double c133, c56, cm13, e6, fl, pad; };
+inline WenoK weno_constants() { return {13.0 / 3.0, 5.0 / 6.0, -1.0 / 3.0, 4.0e-6, 1.0e-70, 0.0}; }
+
+// stored coefficient components and phi^n staged in shared memory next to the phi ring
+struct AuxList {
+    int n;                 // number of staged scalar tiles per plane
+    int first[4];          // first aux index of term k (-1: not staged)
+    int p0;                // aux index of phi^n / corr (-1: none)
+    const void* src[8];    // box pointers (no ghost planes before the first owned node; same strides as the state)
+    WenoK wk;              // see WenoK
+};
+
+// lsm_pair3d.cu (3-D single-term WENO5 advection, x-pair threads).  cudaErrorNotSupported -> use the general tiled kernel.
+template <class T> cudaError_t launch_stage_pair3d(const StageParams<T>& P, const AuxList& A, cudaStream_t s);
+
 // lsm_tiled.cu (performance kernels).  Returns cudaErrorNotSupported when the configuration is
 // not covered, in which case the caller uses the generic kernel.
-template <class T> cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, cudaStream_t s);
+template <class T> cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, cudaStream_t s, bool allow_pair = true, int* used_pair = nullptr);
 template <class T> bool stage_tiled_supported(int ndim, const StageParams<T>& P);
 
 }  // namespace lsm

@@ -1,0 +1,514 @@
+// lsm_pair3d.cu — the headline kernel: one fused RK stage of 3-D WENO5 advection (BASELINE configs 3 and the
+// single-term Float32/Float64 3-D advection runs), re-designed around the measured issue model of round 1
+// (a Float64 instruction costs two issue slots, everything else one, and the kernel is issue bound):
+//
+//   * every thread owns TWO ADJACENT x nodes (i, i+1) of one row (RY = 1) or of two adjacent rows (RY = 2) and
+//     marches along z.  All shared-memory traffic is 128-bit (LDS.128 / STG.128 for Float64 pairs): one load
+//     serves both nodes, so a node costs ~10 shared loads per stage instead of 20, and the x differences (and,
+//     for RY = 2, the y differences) that neighbouring nodes have in common are computed once
+//     (derivatives.jl:89-121 evaluates ϕ[I-3..I+3] per node; adjacent nodes share 6 of their 7 samples);
+//   * the upwind side is resolved by BRANCHING on the sign bits of u·g(t) for the pair — the velocity is smooth,
+//     so warps are almost always uniform — instead of address arithmetic per sample: each side's code reads its
+//     samples at immediate offsets, and the mixed case (a sign change inside the pair or the warp) simply diverges;
+//   * EVERY tile is filled by TMA (cp.async.bulk.tensor.3d + mbarrier), one elected thread per plane; tiles that
+//     touch the x / y boundary get zero-filled out-of-range cells from the TMA unit and a LAZY ghost fix-up: the
+//     ghost cells of plane z+1 (an index map with weight 1 for periodic / Neumann / symmetry,
+//     boundaryconditions.jl:107-153) are fetched from their remapped global address while plane z is being
+//     computed and stored before the barrier.  Ghost planes in z are whole-plane index remaps of the TMA coordinate.
+//
+// The arithmetic is the SAME sequence of operations as lsm_tiled.cu's weno5_up / stage combination, so the two
+// kernels agree bit for bit (tests/test_gpu_parity.py::test_pair_kernel_bitwise_vs_tiled) and both stay within
+// 1e-10 of the oracle after 100 RK3 steps.
+#include "lsm_tile_util.cuh"
+
+namespace lsm {
+
+namespace {
+
+template <class T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+// 128-bit (Float64 pair) / 64-bit (Float32 pair) shared-memory load from a 32-bit shared-window address.  Explicit addresses keep
+// the per-thread base in ONE register for the whole plane loop (the compiler otherwise re-derives element offsets -> byte
+// addresses in every evaluation block: ~19 integer instructions per node, measured with tools/ncu_opmix.py).
+__device__ __forceinline__ double2 lds_pair(unsigned addr, double) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_pair(unsigned addr, float) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+
+template <class T, int RY, int NT>
+struct PairGeom {
+    static constexpr int BX = 64;                 // nodes per tile row: 32 lanes x 2 adjacent nodes
+    static constexpr int TYT = NT / 32;           // thread rows
+    static constexpr int BY = TYT * RY;           // tile rows
+    static constexpr int XL = 4;                  // a TMA box starts at a 16-byte aligned element: 4 columns left of x0
+    static constexpr int W = BX + 2 * XL;
+    static constexpr int HH = BY + 2 * HAL;
+    static constexpr int PLANE = ((W * HH * (int)sizeof(T) + 127) / 128) * 128 / (int)sizeof(T);     // slot stride (elements), 128 B granules
+    static constexpr int TILE = BX * BY;
+    static constexpr int RING = 2 * HAL + 2;      // planes z-3 .. z+3 and the one in flight
+    static constexpr int NBUF = 2;                // coefficient / phi^n tiles: the plane in use and the one in flight
+    static constexpr int NGC = (6 * HH + 6 * W + NT - 1) / NT;     // ghost candidates per thread (boundary tiles)
+    static size_t smem_bytes(int naux) { return ((size_t)RING * PLANE + (size_t)NBUF * naux * TILE) * sizeof(T) + 128 + 16; }
+};
+
+// The reference's _weno5(v1..v5) (derivatives.jl:61-81) on UNDIVIDED first differences, restructured exactly like
+// weno5_up of lsm_tile_util.cuh (second differences, one reciprocal); returns h * weno.  The function is odd:
+// core(-v5..-v1 reversed) == -core(...) bit for bit, which is what makes the physical-order evaluation below
+// identical to the upwind-ordered one of lsm_tiled.cu.
+template <class T>
+__device__ __forceinline__ double weno_core(const WenoK& K, T v1, T v2, T v3, T v4, T v5);
+
+template <>
+__device__ __forceinline__ double weno_core<double>(const WenoK& K, double d0, double d1, double d2, double d3, double d4) {
+    const double e1 = d1 - d0, e2 = d2 - d1, e3 = d3 - d2, e4 = d4 - d3;
+    const double m = absmax5_hi(d0, d1, d2, d3, d4);
+    const double eps = fma(K.e6, m * m, K.fl);
+    const double c133 = K.c133;
+    const double t1a = e2 - e1, t1b = e3 - e2, t1c = e4 - e3;
+    const double t2a = fma(3.0, e2, -e1), t2b = e2 + e3, t2c = fma(-3.0, e3, e4);
+    const double b1 = fma(t2a, t2a, fma(c133, t1a * t1a, eps));
+    const double b2 = fma(t2b, t2b, fma(c133, t1b * t1b, eps));
+    const double b3 = fma(t2c, t2c, fma(c133, t1c * t1c, eps));
+    const double p12 = b1 * b2, p13 = b1 * b3, p23 = b2 * b3;
+    const double w1 = p23 * p23, w2 = p13 * p13, w3 = p12 * p12;
+    const double den = fma(3.0, w3, fma(6.0, w2, w1));
+    const double G1 = fma(K.c56, e2, K.cm13 * e1);
+    const double G2 = fma(2.0, e3, e2);
+    const double G3 = fma(2.0, e3, -0.5 * e4);
+    const double num = fma(w3, G3, fma(w2, G2, w1 * G1));
+    return fma(num, fast_rcp<1>(den), d2);
+}
+
+// Float32 fields: all-FP32 evaluation with the differences normalised by 1/max|d| (see weno5_up<float>)
+template <>
+__device__ __forceinline__ double weno_core<float>(const WenoK&, float d0, float d1, float d2, float d3, float d4) {
+    const float e1 = d1 - d0, e2 = d2 - d1, e3 = d3 - d2, e4 = d4 - d3;
+    const float m = fmaxf(fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fmaxf(fabsf(d2), fabsf(d3))), fabsf(d4));
+    const float im = m > 0.f ? __frcp_rn(m) : 0.f;
+    const float s1 = e1 * im, s2 = e2 * im, s3 = e3 * im, s4 = e4 * im;
+    const float c133 = 13.0f / 3.0f;
+    const float t1a = s2 - s1, t1b = s3 - s2, t1c = s4 - s3;
+    const float t2a = fmaf(3.0f, s2, -s1), t2b = s2 + s3, t2c = fmaf(-3.0f, s3, s4);
+    const float b1 = fmaf(t2a, t2a, fmaf(c133, t1a * t1a, 4.0e-6f));
+    const float b2 = fmaf(t2b, t2b, fmaf(c133, t1b * t1b, 4.0e-6f));
+    const float b3 = fmaf(t2c, t2c, fmaf(c133, t1c * t1c, 4.0e-6f));
+    const float p12 = b1 * b2, p13 = b1 * b3, p23 = b2 * b3;
+    const float w1 = p23 * p23, w2 = p13 * p13, w3 = p12 * p12;
+    const float den = fmaf(3.0f, w3, fmaf(6.0f, w2, w1));
+    const float G1 = fmaf(5.0f / 6.0f, e2, (-1.0f / 3.0f) * e1);
+    const float G2 = fmaf(2.0f, e3, e2);
+    const float G3 = fmaf(2.0f, e3, -0.5f * e4);
+    const float num = fmaf(w3, G3, fmaf(w2, G2, w1 * G1));
+    return double(fmaf(num, __frcp_rn(den), d2));
+}
+
+// h * (the upwind-biased WENO5 derivative) at two nodes A and B along one dimension.  a[k] / b[k] is phi at offset k - 3 from
+// node A / B; xa / xb carries sign(u * g) of the node in bit 31 (set: plus-biased stencil, derivatives.jl:109-121; clear:
+// minus-biased, :89-101).  When B is A's neighbour along the dimension the caller passes b[k] = a[k + 1] and the common
+// differences are shared by the compiler's value numbering.
+template <class T>
+__device__ __forceinline__ void pair_eval(const WenoK& K, const T (&a)[7], const T (&b)[7], int xa, int xb, double& WA, double& WB) {
+    if ((xa | xb) >= 0) {                 // both minus-biased: D-(I-2 .. I+2) = first differences -3 .. 1
+        WA = weno_core<T>(K, T(a[1] - a[0]), T(a[2] - a[1]), T(a[3] - a[2]), T(a[4] - a[3]), T(a[5] - a[4]));
+        WB = weno_core<T>(K, T(b[1] - b[0]), T(b[2] - b[1]), T(b[3] - b[2]), T(b[4] - b[3]), T(b[5] - b[4]));
+    } else if ((xa & xb) < 0) {           // both plus-biased: D+(I+2), D+(I+1), D+(I), D+(I-1), D+(I-2)
+        WA = weno_core<T>(K, T(a[6] - a[5]), T(a[5] - a[4]), T(a[4] - a[3]), T(a[3] - a[2]), T(a[2] - a[1]));
+        WB = weno_core<T>(K, T(b[6] - b[5]), T(b[5] - b[4]), T(b[4] - b[3]), T(b[3] - b[2]), T(b[2] - b[1]));
+    } else {                              // a sign change inside the pair: upwind-ordered samples per node (odd symmetry of the evaluation)
+        const bool ma = xa >= 0, mb = xb >= 0;
+        T qa[6], qb[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { qa[k] = ma ? a[k] : a[6 - k]; qb[k] = mb ? b[k] : b[6 - k]; }
+        const double wa = weno_core<T>(K, T(qa[1] - qa[0]), T(qa[2] - qa[1]), T(qa[3] - qa[2]), T(qa[4] - qa[3]), T(qa[5] - qa[4]));
+        const double wb = weno_core<T>(K, T(qb[1] - qb[0]), T(qb[2] - qb[1]), T(qb[3] - qb[2]), T(qb[4] - qb[3]), T(qb[5] - qb[4]));
+        WA = ma ? wa : -wa;
+        WB = mb ? wb : -wb;
+    }
+}
+
+// CK: COEF_FIELD (stored velocity, staged by TMA next to the phi ring) or COEF_SEPARABLE (u_d = s_d X_d[i] Y_d[j] Z_d[k] from tables).
+// SB: static RK base mode (SB_* of lsm_tile_util.cuh).  FCFL: also reduce the next step's CFL maximum (see StageParams).
+template <class T, int RY, int NT, int CK, bool FCFL, int SB>
+__global__ void __launch_bounds__(NT, 2)
+pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ AuxList A, const __grid_constant__ TmaMaps M, const int cz) {
+    using G = PairGeom<T, RY, NT>;
+    using V2 = typename Vec2<T>::type;
+    constexpr int RING = G::RING, W = G::W, PLANE = G::PLANE, TILE = G::TILE;
+    constexpr bool HAS_P0 = SB == SB_S2 || SB == SB_S3 || SB == SB_P0;
+    constexpr bool HAS_OUT2 = SB == SB_IN_OUT2;
+    constexpr int NVEL = CK == COEF_FIELD ? 3 : 0;
+    constexpr int NAUX = NVEL + (HAS_P0 ? 1 : 0);
+    constexpr unsigned PHI_BYTES = (unsigned)(W * G::HH * sizeof(T));
+    constexpr unsigned AUX_BYTES = (unsigned)(NAUX * TILE * sizeof(T));
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char* const sm128 = smem_raw + ((128u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u);
+    T* const ring = reinterpret_cast<T*>(sm128);
+    T* const aux = ring + (size_t)RING * PLANE;                      // [NBUF][NAUX][TILE]
+    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(aux + (size_t)G::NBUF * NAUX * TILE);
+
+    const int n0 = P.in.n[0], n1 = P.in.n[1], n2 = P.in.n[2];
+    const long vs1 = P.in.s1, vs2 = P.in.s2;
+    const T* __restrict__ const vp = P.in.p;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * 32 + tx;
+    const int x0 = blockIdx.x * G::BX, y0 = blockIdx.y * G::BY;
+    const int zbeg = P.r0 + blockIdx.z * cz;
+    const int zend = min(P.r1, zbeg + cz);
+    if (zbeg >= zend) return;
+    const int kzl = P.in.bc[2][0].kind, kzh = P.in.bc[2][1].kind;
+    const bool leader = tid == 0;
+
+    auto issue_phi = [&](int z, int off) {                        // off: BYTE offset of the destination slot
+        tma_load_3d(reinterpret_cast<unsigned char*>(ring) + off, &M.phi, x0 - G::XL, y0 - HAL, remap_index(z, n2, kzl, kzh) + P.in.halo, bar);
+    };
+    auto issue_aux = [&](int z, int boff) {                       // boff: BYTE offset of the destination buffer
+#pragma unroll
+        for (int a = 0; a < NAUX; ++a) tma_load_3d(reinterpret_cast<unsigned char*>(aux) + boff + a * TILE * (int)sizeof(T), &M.aux[a], x0, y0, z, bar);
+    };
+
+    if (leader) mbar_init(bar, 1);
+    __syncthreads();
+    if (leader) {
+        mbar_expect_tx(bar, (2 * HAL + 1) * PHI_BYTES + AUX_BYTES);
+        for (int p = 0; p <= 2 * HAL; ++p) issue_phi(zbeg - HAL + p, p * PLANE * (int)sizeof(T));
+        issue_aux(zbeg, 0);
+    }
+
+    // ---- loop invariants (computed while the first planes are in flight) ------------------------------------------------
+    // ghost cells of a boundary tile: candidate c of this thread -> (source offset inside a plane, destination offset inside a slot)
+    const bool need_fix = (x0 == 0) || (x0 + G::BX + HAL > n0) || (y0 < HAL) || (y0 + G::BY + HAL > n1);
+    int gsrc[G::NGC], gdst[G::NGC];
+#pragma unroll
+    for (int g = 0; g < G::NGC; ++g) { gsrc[g] = -1; gdst[g] = 0; }
+    if (need_fix) {
+#pragma unroll
+        for (int g = 0; g < G::NGC; ++g) {
+            const int c = tid + g * NT;
+            int col = -1, row = -1;
+            if (c < 6 * G::HH) {                                   // x ghost columns: 3 left of the grid, 3 right of it, every row of the box
+                const int side = c / (3 * G::HH), k = (c % (3 * G::HH)) / G::HH;
+                row = c % G::HH;
+                const int gx = side == 0 ? -1 - k : n0 + k;
+                col = gx - (x0 - G::XL);
+            } else if (c < 6 * G::HH + 6 * W) {                    // y ghost rows: 3 below the grid, 3 above it, every column of the box
+                const int c2 = c - 6 * G::HH;
+                const int side = c2 / (3 * W), k = (c2 % (3 * W)) / W;
+                col = c2 % W;
+                const int gy = side == 0 ? -1 - k : n1 + k;
+                row = gy - (y0 - HAL);
+            }
+            if (col >= 0 && col < W && row >= 0 && row < G::HH) {
+                const int gx = x0 - G::XL + col, gy = y0 - HAL + row;
+                if (gx >= -HAL && gx < n0 + HAL && gy >= -HAL && gy < n1 + HAL) {
+                    const int sx = min(max(remap_index(gx, n0, P.in.bc[0][0].kind, P.in.bc[0][1].kind), 0), n0 - 1);
+                    const int sy = min(max(remap_index(gy, n1, P.in.bc[1][0].kind, P.in.bc[1][1].kind), 0), n1 - 1);
+                    gsrc[g] = sx + sy * (int)vs1;
+                    gdst[g] = row * W + col;
+                }
+            }
+        }
+    }
+    // this thread's nodes: columns i, i+1 of rows j0 .. j0+RY-1
+    const int i = x0 + 2 * tx;
+    const int j0 = y0 + ty * RY;
+    const int sc = (ty * RY + HAL) * W + G::XL + 2 * tx;          // element offset of node (i, j0) inside a ring slot (even: 16-byte aligned pairs)
+    const int st = (ty * RY) * G::BX + 2 * tx;                    // same inside an aux tile
+    bool act[RY];
+#pragma unroll
+    for (int r = 0; r < RY; ++r) act[r] = i < n0 && (j0 + r) < n1;
+    const double g = P.terms[0].scaled ? P.terms[0].g : 1.0;
+    const int ghi = __double2hiint(g);
+    const double gih[3] = {g * (1.0 / P.h[0]), g * (1.0 / P.h[1]), g * (1.0 / P.h[2])};
+    // separable velocity: the x-y factor of every node is a loop invariant (same product order as the stored tables)
+    double pxy[RY][2][3];
+    if (CK == COEF_SEPARABLE) {
+#pragma unroll
+        for (int r = 0; r < RY; ++r)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int ii = min(i + c, n0 - 1), jj = min(j0 + r, n1 - 1);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) pxy[r][c][d] = (P.terms[0].cval[d] * __ldg(P.terms[0].tab[d][0] + ii)) * __ldg(P.terms[0].tab[d][1] + jj);
+            }
+    }
+    // The five WENO constants that do not fit an instruction immediate are made opaque to ptxas (threadIdx.z is always 0, which
+    // the compiler cannot know): as plain kernel parameters it re-materialises them from the constant bank with ~12 moves in every
+    // one of the six evaluation blocks of a plane (36 issue slots per node, measured in SASS); this way they stay in 10 registers.
+    const double zopq = __longlong_as_double((long long)threadIdx.z);
+    WenoK KR;
+    KR.c133 = A.wk.c133 + zopq; KR.c56 = A.wk.c56 + zopq; KR.cm13 = A.wk.cm13 + zopq; KR.e6 = A.wk.e6 + zopq; KR.fl = A.wk.fl + zopq; KR.pad = 0.0;
+    long lin = (long)i + (long)j0 * vs1 + (long)zbeg * vs2;       // output / phi^n element offset of node (i, j0, z)
+    unsigned long long cfl_best = 0ULL;
+
+    mbar_wait(bar, 0);
+    unsigned phase = 1;
+    if (need_fix) {                                                // ghosts of the first plane (slot HAL): fetched and stored on the spot
+#pragma unroll
+        for (int gk = 0; gk < G::NGC; ++gk)
+            if (gsrc[gk] >= 0) ring[HAL * PLANE + gdst[gk]] = vp[(long)zbeg * vs2 + gsrc[gk]];
+    }
+    __syncthreads();
+
+    constexpr int ES = (int)sizeof(T);
+    constexpr int ABUF = NAUX * TILE * ES;                         // bytes of one aux buffer
+    int zo[2 * HAL + 1];                                           // BYTE offsets of the slots of planes z-3 .. z+3 (block-uniform)
+#pragma unroll
+    for (int k = 0; k <= 2 * HAL; ++k) zo[k] = k * PLANE * ES;
+    int onew = (2 * HAL + 1) * PLANE * ES;                         // slot receiving plane z + 4
+    int ab = 0;                                                    // byte offset of the aux buffer of plane z (0 or ABUF)
+    const unsigned sc_a = (unsigned)__cvta_generic_to_shared(ring) + (unsigned)(sc * ES);      // node (i, j0) in slot 0
+    const unsigned st_a = (unsigned)__cvta_generic_to_shared(aux) + (unsigned)(st * ES);       // node (i, j0) in aux tile 0 of buffer 0
+
+    for (int z = zbeg; z < zend; ++z) {
+        const bool lp = z + HAL + 1 <= zend - 1 + HAL;             // plane z+4 will be read by a later iteration
+        const bool la = z + 1 < zend;
+        if (leader && (lp || la)) {
+            mbar_expect_tx(bar, (lp ? PHI_BYTES : 0u) + (la ? AUX_BYTES : 0u));
+            if (lp) issue_phi(z + HAL + 1, onew);
+            if (la) issue_aux(z + 1, ABUF - ab);
+        }
+        // ghost cells of plane z+1 (arrived three iterations ago, current in the next one): fetch now, store before the barrier
+        T gval[G::NGC];
+        const bool fix = need_fix && la;
+        if (fix) {
+            const T* src = vp + (long)(z + 1) * vs2;
+#pragma unroll
+            for (int gk = 0; gk < G::NGC; ++gk) gval[gk] = gsrc[gk] >= 0 ? __ldg(src + gsrc[gk]) : T(0);
+        }
+
+        const unsigned cur = sc_a + (unsigned)zo[HAL];
+        const unsigned auxz = st_a + (unsigned)ab;
+        if (act[0]) {
+            double H[RY][2];
+            double uraw[RY][2][3];
+            V2 cc[RY];
+            // ---- x: the two nodes of a row share 6 of their 7 samples
+#pragma unroll
+            for (int r = 0; r < RY; ++r) {
+                const unsigned row = cur + r * W * ES;
+                const V2 m2 = lds_pair(row - 4 * ES, T()), m1 = lds_pair(row - 2 * ES, T()), c0 = lds_pair(row, T()),
+                         p1 = lds_pair(row + 2 * ES, T()), p2 = lds_pair(row + 4 * ES, T());
+                cc[r] = c0;
+                const T a[7] = {m2.y, m1.x, m1.y, c0.x, c0.y, p1.x, p1.y};
+                const T b[7] = {m1.x, m1.y, c0.x, c0.y, p1.x, p1.y, p2.x};
+                double ua, ub;
+                if (CK == COEF_FIELD) {
+                    const V2 u = lds_pair(auxz + r * G::BX * ES, T());
+                    ua = double(u.x); ub = double(u.y);
+                } else { ua = pxy[r][0][0] * __ldg(P.terms[0].tab[0][2] + z); ub = pxy[r][1][0] * __ldg(P.terms[0].tab[0][2] + z); }
+                uraw[r][0][0] = ua; uraw[r][1][0] = ub;
+                double wa, wb;
+                pair_eval<T>(KR, a, b, __double2hiint(ua) ^ ghi, __double2hiint(ub) ^ ghi, wa, wb);
+                H[r][0] = (ua * gih[0]) * wa;
+                H[r][1] = (ub * gih[0]) * wb;
+            }
+            // ---- y
+            {
+                V2 yv[7 + RY - 1];
+#pragma unroll
+                for (int k = 0; k < 7 + RY - 1; ++k) yv[k] = (k >= HAL && k < HAL + RY) ? cc[k - HAL] : lds_pair(cur + (k - HAL) * W * ES, T());
+                double u[RY][2];
+#pragma unroll
+                for (int r = 0; r < RY; ++r) {
+                    if (CK == COEF_FIELD) {
+                        const V2 uu = lds_pair(auxz + (TILE + r * G::BX) * ES, T());
+                        u[r][0] = double(uu.x); u[r][1] = double(uu.y);
+                    } else { u[r][0] = pxy[r][0][1] * __ldg(P.terms[0].tab[1][2] + z); u[r][1] = pxy[r][1][1] * __ldg(P.terms[0].tab[1][2] + z); }
+                    uraw[r][0][1] = u[r][0]; uraw[r][1][1] = u[r][1];
+                }
+                if (RY == 1) {
+                    const T a[7] = {yv[0].x, yv[1].x, yv[2].x, yv[3].x, yv[4].x, yv[5].x, yv[6].x};
+                    const T b[7] = {yv[0].y, yv[1].y, yv[2].y, yv[3].y, yv[4].y, yv[5].y, yv[6].y};
+                    double wa, wb;
+                    pair_eval<T>(KR, a, b, __double2hiint(u[0][0]) ^ ghi, __double2hiint(u[0][1]) ^ ghi, wa, wb);
+                    H[0][0] = fma(u[0][0] * gih[1], wa, H[0][0]);
+                    H[0][1] = fma(u[0][1] * gih[1], wb, H[0][1]);
+                } else {
+                    // rows j0, j0+1 of the same column share their samples
+                    const T a0[7] = {yv[0].x, yv[1].x, yv[2].x, yv[3].x, yv[4].x, yv[5].x, yv[6].x};
+                    const T a1[7] = {yv[1].x, yv[2].x, yv[3].x, yv[4].x, yv[5].x, yv[6].x, yv[6 + RY - 1].x};
+                    const T b0[7] = {yv[0].y, yv[1].y, yv[2].y, yv[3].y, yv[4].y, yv[5].y, yv[6].y};
+                    const T b1[7] = {yv[1].y, yv[2].y, yv[3].y, yv[4].y, yv[5].y, yv[6].y, yv[6 + RY - 1].y};
+                    double w00, w10, w01, w11;
+                    pair_eval<T>(KR, a0, a1, __double2hiint(u[0][0]) ^ ghi, __double2hiint(u[RY - 1][0]) ^ ghi, w00, w10);
+                    pair_eval<T>(KR, b0, b1, __double2hiint(u[0][1]) ^ ghi, __double2hiint(u[RY - 1][1]) ^ ghi, w01, w11);
+                    H[0][0] = fma(u[0][0] * gih[1], w00, H[0][0]);
+                    H[0][1] = fma(u[0][1] * gih[1], w01, H[0][1]);
+                    H[RY - 1][0] = fma(u[RY - 1][0] * gih[1], w10, H[RY - 1][0]);
+                    H[RY - 1][1] = fma(u[RY - 1][1] * gih[1], w11, H[RY - 1][1]);
+                }
+            }
+            // ---- z: the column of every node through the ring
+#pragma unroll
+            for (int r = 0; r < RY; ++r) {
+                V2 zv[7];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) zv[k] = k == HAL ? cc[r] : lds_pair(sc_a + (unsigned)zo[k] + r * W * ES, T());
+                const T a[7] = {zv[0].x, zv[1].x, zv[2].x, zv[3].x, zv[4].x, zv[5].x, zv[6].x};
+                const T b[7] = {zv[0].y, zv[1].y, zv[2].y, zv[3].y, zv[4].y, zv[5].y, zv[6].y};
+                double ua, ub;
+                if (CK == COEF_FIELD) {
+                    const V2 u = lds_pair(auxz + (2 * TILE + r * G::BX) * ES, T());
+                    ua = double(u.x); ub = double(u.y);
+                } else { ua = pxy[r][0][2] * __ldg(P.terms[0].tab[2][2] + z); ub = pxy[r][1][2] * __ldg(P.terms[0].tab[2][2] + z); }
+                uraw[r][0][2] = ua; uraw[r][1][2] = ub;
+                double wa, wb;
+                pair_eval<T>(KR, a, b, __double2hiint(ua) ^ ghi, __double2hiint(ub) ^ ghi, wa, wb);
+                H[r][0] = fma(ua * gih[2], wa, H[r][0]);
+                H[r][1] = fma(ub * gih[2], wb, H[r][1]);
+            }
+            // ---- RK stage combination (timestepping.jl:128-202) and the pair store
+#pragma unroll
+            for (int r = 0; r < RY; ++r) {
+                if (r > 0 && !act[r]) break;
+                T xb[2] = {cc[r].x, cc[r].y};
+                if (HAS_P0) {
+                    const V2 pn = lds_pair(auxz + (NVEL * TILE + r * G::BX) * ES, T());
+                    const T pv[2] = {pn.x, pn.y};
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (SB == SB_S2) xb[c] = T(fma(0.75, double(pv[c]), 0.25 * double(xb[c])));       // timestepping.jl:183
+                        else if (SB == SB_S3) xb[c] = div3(T(pv[c] + T(2) * xb[c]));                       // timestepping.jl:194
+                        else xb[c] = pv[c];                                                                // RK2 S2 (corr)
+                    }
+                }
+                V2 o;
+                o.x = T(fma(-P.c, H[r][0], double(xb[0])));
+                o.y = T(fma(-P.c, H[r][1], double(xb[1])));
+                *reinterpret_cast<V2*>(P.out + lin + r * vs1) = o;
+                if (HAS_OUT2) {
+                    V2 o2;
+                    o2.x = T(fma(-P.c2, H[r][0], double(cc[r].x)));
+                    o2.y = T(fma(-P.c2, H[r][1], double(cc[r].y)));
+                    *reinterpret_cast<V2*>(P.out2 + lin + r * vs1) = o2;
+                }
+                if (FCFL) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        // cheap estimate sum_d |u_d| |g_stage| / h_d against the candidate bound; candidates evaluate the reference
+                        // expression bit for bit (levelsetterms.jl:90-96)
+                        const double sest = (fabs(uraw[r][c][0] * gih[0]) + fabs(uraw[r][c][1] * gih[1])) + fabs(uraw[r][c][2] * gih[2]);
+                        if (!(sest < P.cfl_tau)) {
+                            double sx = 0.0;
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) {
+                                const double q = __ddiv_rn(fabs(__dmul_rn(uraw[r][c][d], P.cfl_g)), P.h[d]);
+                                sx = d == 0 ? q : __dadd_rn(sx, q);
+                            }
+                            const unsigned long long bits = isnan(sx) ? 0x7FF8000000000000ULL : (unsigned long long)__double_as_longlong(sx);
+                            cfl_best = bits > cfl_best ? bits : cfl_best;
+                        }
+                    }
+                }
+            }
+        }
+        if (fix) {
+            T* dst = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ring) + zo[HAL + 1]);
+#pragma unroll
+            for (int gk = 0; gk < G::NGC; ++gk)
+                if (gsrc[gk] >= 0) dst[gdst[gk]] = gval[gk];
+        }
+        if (lp || la) { mbar_wait(bar, phase); phase ^= 1u; }
+        __syncthreads();
+        {
+            const int freed = zo[0];                               // plane z-3 is dead: its slot receives plane z+5 in the next iteration
+#pragma unroll
+            for (int k = 0; k < 2 * HAL; ++k) zo[k] = zo[k + 1];
+            zo[2 * HAL] = onew;
+            onew = freed;
+        }
+        ab = ABUF - ab;
+        lin += vs2;
+    }
+    if (FCFL) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, cfl_best, o);
+            cfl_best = other > cfl_best ? other : cfl_best;
+        }
+        if ((tid & 31) == 0 && cfl_best) atomicMax(P.cfl_out, cfl_best);
+    }
+}
+
+#ifndef LSM_PAIR_RY
+#define LSM_PAIR_RY 1
+#define LSM_PAIR_NT 256
+#endif
+
+template <class T, int CK, bool FCFL, int SB>
+cudaError_t launch_pair(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
+    constexpr int RY = LSM_PAIR_RY, NT = LSM_PAIR_NT;
+    using G = PairGeom<T, RY, NT>;
+    auto kern = pair3d_kernel<T, RY, NT, CK, FCFL, SB>;
+    constexpr bool HAS_P0 = SB == SB_S2 || SB == SB_S3 || SB == SB_P0;
+    constexpr int NAUX = (CK == COEF_FIELD ? 3 : 0) + (HAS_P0 ? 1 : 0);
+    const size_t smem = G::smem_bytes(NAUX);
+    static size_t attr_smem[16] = {};
+    { cudaError_t e = ensure_dyn_smem(kern, smem, attr_smem); if (e != cudaSuccess) return e; }
+    const View<T>& v = P.in;
+    TmaMaps M;
+    M.enabled = 1;
+    const T* base = v.p - (long)v.halo * v.s2;
+    if ((uintptr_t)base % 16 != 0 || !cached_map3<T>(&M.phi, base, v.n[0], v.n[1], (long)v.n[2] + 2L * v.halo, G::W, G::HH)) return cudaErrorNotSupported;
+    for (int a = 0; a < NAUX; ++a)
+        if ((uintptr_t)A.src[a] % 16 != 0 || !cached_map3<T>(&M.aux[a], A.src[a], v.n[0], v.n[1], v.n[2], G::BX, G::BY)) return cudaErrorNotSupported;
+    const int nr = P.r1 - P.r0;
+    const int cz = nr >= 128 ? 64 : (nr >= 32 ? 32 : nr);
+    dim3 block(32, NT / 32), grid((v.n[0] + G::BX - 1) / G::BX, (v.n[1] + G::BY - 1) / G::BY, (nr + cz - 1) / cz);
+    kern<<<grid, block, smem, s>>>(P, A, M, cz);
+    return cudaGetLastError();
+}
+
+template <class T, int CK, bool FCFL>
+cudaError_t launch_pair_sb(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
+    constexpr int SP0 = CK == COEF_FIELD ? 3 : 0;
+    if (A.p0 >= 0 && A.p0 != SP0) return cudaErrorNotSupported;
+    if (P.base == BASE_IN && !P.p0) {
+        if (!P.out2) return launch_pair<T, CK, FCFL, SB_IN>(P, A, s);
+        if (!FCFL) return launch_pair<T, CK, false, SB_IN_OUT2>(P, A, s);
+    }
+    if (P.base == BASE_RK3_S2 && P.p0 && !P.out2 && !FCFL) return launch_pair<T, CK, false, SB_S2>(P, A, s);
+    if (P.base == BASE_RK3_S3 && P.p0 && !P.out2) return launch_pair<T, CK, FCFL, SB_S3>(P, A, s);
+    if (P.base == BASE_P0 && P.p0 && !P.out2) return launch_pair<T, CK, FCFL, SB_P0>(P, A, s);
+    return cudaErrorNotSupported;
+}
+
+}  // namespace
+
+// Single-term 3-D WENO5 advection with index-map boundary conditions on a TMA-compatible box; anything else reports
+// cudaErrorNotSupported and the caller takes the general tiled kernel.
+template <class T>
+cudaError_t launch_stage_pair3d(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
+    if (pair_kernel_disabled() || tma_disabled() || !encode_tiled_fn()) return cudaErrorNotSupported;
+    if (P.nterms != 1) return cudaErrorNotSupported;
+    const TermDev& t0 = P.terms[0];
+    if (t0.kind != TERM_ADVECTION || t0.scheme != SCHEME_WENO5) return cudaErrorNotSupported;
+    const View<T>& v = P.in;
+    if ((v.n[0] * sizeof(T)) % 16 != 0 || v.n[0] < 8 || v.n[1] < 8 || v.n[2] < 4) return cudaErrorNotSupported;
+    if ((long)v.n[0] * v.n[1] >= (1L << 31)) return cudaErrorNotSupported;
+    for (int d = 0; d < 3; ++d)
+        for (int sd = 0; sd < 2; ++sd) {
+            const BCDev& b = v.bc[d][sd];
+            const bool index_map = b.kind == BC_PERIODIC || b.kind == BC_SYMMETRY || (b.kind == BC_EXTRAP && b.P == 0) || (b.kind == BC_HALO && d == 2);
+            if (!index_map) return cudaErrorNotSupported;
+        }
+    if (t0.coef_kind == COEF_FIELD && A.first[0] == 0 && !t0.coef_f64)
+        return P.cfl_out ? launch_pair_sb<T, COEF_FIELD, true>(P, A, s) : launch_pair_sb<T, COEF_FIELD, false>(P, A, s);
+    if (t0.coef_kind == COEF_SEPARABLE)
+        return P.cfl_out ? launch_pair_sb<T, COEF_SEPARABLE, true>(P, A, s) : launch_pair_sb<T, COEF_SEPARABLE, false>(P, A, s);
+    return cudaErrorNotSupported;
+}
+
+template cudaError_t launch_stage_pair3d<float>(const StageParams<float>&, const AuxList&, cudaStream_t);
+template cudaError_t launch_stage_pair3d<double>(const StageParams<double>&, const AuxList&, cudaStream_t);
+
+}  // namespace lsm

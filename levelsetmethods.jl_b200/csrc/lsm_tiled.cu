@@ -27,13 +27,7 @@
 //
 // Compiled with FMA contraction ON.  Parity with the CPU oracle is checked in tests/ (<= 1e-10 after
 // 100 RK3 steps in Float64, <= 1e-4 in Float32).
-#include <type_traits>
-#include <cstdint>
-#include <cstdlib>
-#include <cuda.h>          // CUtensorMap + enums only; cuTensorMapEncodeTiled is looked up at run time (no libcuda link)
-#include "lsm_dev.cuh"
-#include "lsm_bc.cuh"
-#include "lsm_kernels.h"
+#include "lsm_tile_util.cuh"
 
 namespace lsm {
 
@@ -46,180 +40,6 @@ namespace {
 #define LSM_MINB_EIK 3    // Eikonal kernel: latency-bound at 16 warps/SM (ncu: 'wait' + short-scoreboard stalls lead); 3 blocks of 74 KB fit.
                           // Also the Float32 advection kernels (45 KB each; the fused-CFL variant otherwise takes 84 registers -> 2 blocks)
 #endif
-constexpr int HAL = 3;           // WENO5 reach; every term's stencil fits in it
-
-enum : int { M_ADV_WENO = 1, M_ADV_UPWIND = 2, M_NORMAL = 4, M_CURV = 8, M_EIK = 16, M_ALL = 31 };
-
-__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc, int bytes8) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    if (bytes8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-    else        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// ---- TMA (cp.async.bulk.tensor) + mbarrier: one elected thread copies a whole (tile + halo) plane -----------
-struct TmaMaps {
-    int enabled;                       // tensor maps below are valid
-    int _pad[15];
-    alignas(64) CUtensorMap phi;       // stage input incl. its ghost planes: dims (n0, n1, halo + n2 + halo)
-    alignas(64) CUtensorMap aux[8];    // staged coefficient components and phi^n: dims (n0, n1, n2)
-};
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LSM_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LSM_DONE_%=;\n"
-        "bra LSM_WAIT_%=;\n"
-        "LSM_DONE_%=:\n"
-        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2),
-                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-
-// 1/x for a positive normal x: MUFU.RCP64H seed (uses the top 32 bits of x: relative error ~2^-20) + Newton steps.
-// STEPS = 2 gives ~1e-16; STEPS = 1 gives ~1e-12, enough where the quotient is a small correction term
-// (WENO5: W = d2 + num/den with |num/den| <= max|e_k| << |d|).
-template <int STEPS>
-__device__ __forceinline__ double fast_rcp(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#pragma unroll
-    for (int k = 0; k < STEPS; ++k) {
-        const double t = fma(-x, y, 1.0);
-        y = fma(y, t, y);
-    }
-    return y;
-}
-
-// The element of largest magnitude among a..e (exact; only its square is used).  A plain compare-select is
-// DSETP + 2 SEL (~1 DP slot, measured 60 lane-ops/clk/SM for compare-select + add in tools/fp64_peak.cu), whereas
-// fmax() carries NaN-handling code (~3.7 slots).  NaN inputs poison the smoothness indicators anyway.
-__device__ __forceinline__ double absmax5(double a, double b, double c, double d, double e) {
-    double m = a;
-    m = fabs(b) > fabs(m) ? b : m;
-    m = fabs(c) > fabs(m) ? c : m;
-    m = fabs(d) > fabs(m) ? d : m;
-    m = fabs(e) > fabs(m) ? e : m;
-    return m;
-}
-
-// Undivided upwind WENO5: given six samples in upwind order (q3 is the node, q0 the far upwind
-// end), returns h * weno5 of the reference (derivatives.jl:61-121), i.e. the reference value is
-// this divided by h and multiplied by s = sign of the sampling direction.
-//   d_k  = q_{k+1} - q_k            (v_k * h of the reference, up to the global sign s)
-//   e_k  = d_k - d_{k-1}
-//   4*S1 = 13/3 (e2-e1)^2 + (3e2-e1)^2 ; 4*S2 = 13/3 (e3-e2)^2 + (e2+e3)^2 ; 4*S3 = 13/3 (e4-e3)^2 + (e4-3e3)^2
-//   b_k  = 4 h^2 (S_k + eps) = 4*S_k(d) + 4e-6 max(d^2) + floor
-//   w_k  ~ {1,6,3} / b_k^2  ->  result = d2 + (q1 G1 + q2 G2 + q3 G3) / (q1 + 6 q2 + 3 q3),  q1 = (b2 b3)^2 ...
-//   G1 = 5/6 e2 - 1/3 e1 ; G2 = 2 e3 + e2 ; G3 = 2 e3 - 1/2 e4     (6 and 3 folded in)
-// The floor 1e-70 replaces 4e-99*h^2 (which would underflow in the product form).  It only matters
-// where every |d| < ~1e-26, i.e. on numerically flat data, where the result is O(|d|) either way.
-// The five Float64 constants of the evaluation that do not fit an instruction immediate.  They travel in the kernel
-// parameters (constant bank): as literals the compiler re-materialises them with 10 UMOV per node, from the constant bank
-// it takes 3 uniform loads.
-struct WenoK { double c133, c56, cm13, e6, fl, pad; };
-inline WenoK weno_constants() { return {13.0 / 3.0, 5.0 / 6.0, -1.0 / 3.0, 4.0e-6, 1.0e-70, 0.0}; }
-
-template <class T>
-__device__ __forceinline__ double weno5_up(const WenoK& K, T q0, T q1, T q2, T q3, T q4, T q5) {
-    const double d0 = double(T(q1 - q0)), d1 = double(T(q2 - q1)), d2 = double(T(q3 - q2)),
-                 d3 = double(T(q4 - q3)), d4 = double(T(q5 - q4));
-    const double e1 = d1 - d0, e2 = d2 - d1, e3 = d3 - d2, e4 = d4 - d3;
-    const double m = absmax5(d0, d1, d2, d3, d4);
-    const double eps = fma(K.e6, m * m, K.fl);
-    const double c133 = K.c133;
-    const double t1a = e2 - e1, t1b = e3 - e2, t1c = e4 - e3;
-    const double t2a = fma(3.0, e2, -e1), t2b = e2 + e3, t2c = fma(-3.0, e3, e4);
-    const double b1 = fma(t2a, t2a, fma(c133, t1a * t1a, eps));
-    const double b2 = fma(t2b, t2b, fma(c133, t1b * t1b, eps));
-    const double b3 = fma(t2c, t2c, fma(c133, t1c * t1c, eps));
-    const double p12 = b1 * b2, p13 = b1 * b3, p23 = b2 * b3;
-    const double w1 = p23 * p23, w2 = p13 * p13, w3 = p12 * p12;
-    const double den = fma(3.0, w3, fma(6.0, w2, w1));
-    const double G1 = fma(K.c56, e2, K.cm13 * e1);
-    const double G2 = fma(2.0, e3, e2);
-    const double G3 = fma(2.0, e3, -0.5 * e4);
-    const double num = fma(w3, G3, fma(w2, G2, w1 * G1));
-    return fma(num, fast_rcp<1>(den), d2);
-}
-
-// Float32 fields: the same evaluation entirely in FP32 (FFMA issues at <= 1 slot, FP64 at 2; BASELINE tolerance for
-// Float32 is 1e-4 against the oracle, which follows Julia's promotion to Float64 after the first difference).
-// Range safety in FP32: the differences are normalised by 1/max|d| before squaring, so b_k = 4(S_k + eps)/max(d^2)
-// lies in [4e-6, ~1e2], the weights in [1e-22, 1e8], and eps = 1e-6*max(v^2) becomes the exact constant 4e-6
-// (flat data: max|d| = 0 -> all b_k equal -> result d2 = 0, finite).
-template <>
-__device__ __forceinline__ double weno5_up<float>(const WenoK&, float q0, float q1, float q2, float q3, float q4, float q5) {
-    const float d0 = q1 - q0, d1 = q2 - q1, d2 = q3 - q2, d3 = q4 - q3, d4 = q5 - q4;
-    const float e1 = d1 - d0, e2 = d2 - d1, e3 = d3 - d2, e4 = d4 - d3;
-    const float m = fmaxf(fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fmaxf(fabsf(d2), fabsf(d3))), fabsf(d4));
-    const float im = m > 0.f ? __frcp_rn(m) : 0.f;
-    const float s1 = e1 * im, s2 = e2 * im, s3 = e3 * im, s4 = e4 * im;
-    const float c133 = 13.0f / 3.0f;
-    const float t1a = s2 - s1, t1b = s3 - s2, t1c = s4 - s3;
-    const float t2a = fmaf(3.0f, s2, -s1), t2b = s2 + s3, t2c = fmaf(-3.0f, s3, s4);
-    const float b1 = fmaf(t2a, t2a, fmaf(c133, t1a * t1a, 4.0e-6f));
-    const float b2 = fmaf(t2b, t2b, fmaf(c133, t1b * t1b, 4.0e-6f));
-    const float b3 = fmaf(t2c, t2c, fmaf(c133, t1c * t1c, 4.0e-6f));
-    const float p12 = b1 * b2, p13 = b1 * b3, p23 = b2 * b3;
-    const float w1 = p23 * p23, w2 = p13 * p13, w3 = p12 * p12;
-    const float den = fmaf(3.0f, w3, fmaf(6.0f, w2, w1));
-    const float G1 = fmaf(5.0f / 6.0f, e2, (-1.0f / 3.0f) * e1);
-    const float G2 = fmaf(2.0f, e3, e2);
-    const float G3 = fmaf(2.0f, e3, -0.5f * e4);
-    const float num = fmaf(w3, G3, fmaf(w2, G2, w1 * G1));
-    return double(fmaf(num, __frcp_rn(den), d2));
-}
-
-// x / 3 correctly rounded without the generic division sequence (timestepping.jl:194 divides by 3 in the storage type):
-// q0 = RN(x * RN(1/3)), r = x - 3 q0 (exact in an FMA), q = RN(q0 + r * RN(1/3)) is the correctly rounded quotient when the
-// reciprocal is correctly rounded and q0 is within one ulp (Markstein's theorem; 3 has no all-ones significand).
-__device__ __forceinline__ double div3(double x) {
-    const double q = x * (1.0 / 3.0);
-    return fma(fma(-3.0, q, x), 1.0 / 3.0, q);
-}
-__device__ __forceinline__ float div3(float x) {
-    const float q = x * (1.0f / 3.0f);
-    return fmaf(fmaf(-3.0f, q, x), 1.0f / 3.0f, q);
-}
-
-// Static term signature of the multi-term instantiations: TK packs the kind of term k in bits [3k, 3k+3)
-// (SK_* below; TK < 0: kinds are runtime data), COEFK packs its coefficient kind in bits [2k, 2k+2) (COEFK < 0: runtime).
-// static base modes of a launch (template parameter SB; -1 = runtime): BASE_* of lsm_dev.cuh plus the presence of out2
-enum : int { SB_IN = 0, SB_S2 = 1, SB_S3 = 2, SB_IN_OUT2 = 3, SB_P0 = 4 };
-enum : int { SK_ADV_WENO = 0, SK_ADV_UPWIND = 1, SK_NORMAL = 2, SK_CURV = 3, SK_EIK = 4 };
-__host__ __device__ constexpr int sig_kind(int TK, int k) { return TK < 0 || k < 0 ? -1 : ((TK >> (3 * k)) & 7); }
-__host__ __device__ constexpr int sig_coef(int COEFK, int k) { return COEFK < 0 || k < 0 ? -1 : ((COEFK >> (2 * k)) & 3); }
-// first staged aux tile of term k when every FIELD coefficient before it is staged (the launcher checks)
-__host__ __device__ constexpr int sig_first(int TK, int COEFK, int k, int ndim) {
-    int f = 0;
-    for (int j = 0; j < k; ++j)
-        if (sig_coef(COEFK, j) == COEF_FIELD) f += (sig_kind(TK, j) == SK_ADV_WENO || sig_kind(TK, j) == SK_ADV_UPWIND) ? ndim : 1;
-    return f;
-}
-
-// levelsetterms.jl:184-187
-// Same-sign test on the sign bits (LOP3 + ISETP instead of DMUL + DSETP): identical to `x*y > 0` except where the product
-// underflows (|x||y| < 5e-324), where the reference returns 0 and this returns min(|x|,|y|) < 1e-150 — far below any tolerance.
-// x == 0 or y == 0 selects the zero operand, as the reference's 0 result.
-__device__ __forceinline__ double minmod(double x, double y) {
-    const double m = fabs(x) <= fabs(y) ? x : y;
-    return (__double2hiint(x) ^ __double2hiint(y)) < 0 ? 0.0 : m;
-}
 
 template <class T, int NDIM, int TX, int TY, int NY>
 struct TileGeom {
@@ -239,34 +59,6 @@ struct TileGeom {
     static size_t smem_bytes(int naux) { return ((size_t)RING * PLANE + (size_t)NBUF * naux * TILE) * sizeof(T) + 128 + 16; }   // + alignment slack + mbarrier
 };
 
-// stored coefficient components and phi^n staged in shared memory next to the phi ring
-struct AuxList {
-    int n;                 // number of staged scalar tiles per plane
-    int first[4];          // first aux index of term k (-1: not staged)
-    int p0;                // aux index of phi^n / corr (-1: none)
-    const void* src[8];    // box pointers (no ghost planes before the first owned node; same strides as the state)
-    WenoK wk;              // see WenoK
-};
-
-// Ghost index -> stored index for the boundary conditions that are pure index maps with weight 1
-// (boundaryconditions.jl:107-119 periodic wrap, :134-144 with P = 0 i.e. NeumannBC, :146-153 symmetry).
-// Applied independently per dimension this equals the reference's dimension-by-dimension recursion
-// (meshfield.jl:248-260).  BC_HALO sides keep the index (stored ghost plane).  Needs n >= 4.
-__device__ __forceinline__ int remap_index(int i, int n, int kind_lo, int kind_hi) {
-    if (i < 0) {
-        if (kind_lo == BC_PERIODIC) return i + n - 1;
-        if (kind_lo == BC_EXTRAP) return 0;
-        if (kind_lo == BC_SYMMETRY) return -i;
-        return i;
-    }
-    if (i >= n) {
-        if (kind_hi == BC_PERIODIC) return i - n + 1;
-        if (kind_hi == BC_EXTRAP) return n - 1;
-        if (kind_hi == BC_SYMMETRY) return 2 * (n - 1) - i;
-        return i;
-    }
-    return i;
-}
 
 // Fused stage kernel.  MASK = which term kinds the instantiation carries code for; the terms themselves
 // (order, coefficients) are runtime data, applied one after the other like the reference
@@ -681,35 +473,6 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
 #define LSM_MINB 2
 #endif
 
-// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (liblsm_b200 does not link libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-template <class T>
-bool encode_map3(CUtensorMap* m, const void* base, long n0, long n1, long nplanes, int b0, int b1) {
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc) return false;
-    const cuuint64_t dims[3] = {(cuuint64_t)n0, (cuuint64_t)n1, (cuuint64_t)nplanes};
-    const cuuint64_t strides[2] = {(cuuint64_t)n0 * sizeof(T), (cuuint64_t)n0 * n1 * sizeof(T)};
-    const cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1u};
-    const cuuint32_t es[3] = {1u, 1u, 1u};
-    return enc(m, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims,
-               strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
 
 template <class T, int NDIM, int MASK, int NTS, int COEFK, bool REMAP, bool FCFL = false, int TK = -1, int SB = -1>
 cudaError_t launch_tiled(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
@@ -717,21 +480,17 @@ cudaError_t launch_tiled(const StageParams<T>& P, const AuxList& A, cudaStream_t
     using G = TileGeom<T, NDIM, TX, TY, NY>;
     auto kern = stage_tiled_kernel<T, NDIM, MASK, NTS, COEFK, REMAP, FCFL, TX, TY, NY, LSM_MINB, TK, SB>;
     const size_t smem = G::smem_bytes(A.n);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_smem = smem;
-    }
+    static size_t attr_smem[16] = {};
+    { cudaError_t e = ensure_dyn_smem(kern, smem, attr_smem); if (e != cudaSuccess) return e; }
     const View<T>& v = P.in;
     // TMA tensor maps: 3-D, rows a multiple of 16 bytes, 16-byte aligned bases, and a grid big enough to care
     TmaMaps M;
     M.enabled = 0;
-    if (NDIM == 3 && (v.n[0] * sizeof(T)) % 16 == 0 && (long)v.n[0] * v.n[1] * v.n[2] >= 32L * 32 * 32 && !getenv("LSM_B200_NO_TMA")) {
+    if (NDIM == 3 && (v.n[0] * sizeof(T)) % 16 == 0 && (long)v.n[0] * v.n[1] * v.n[2] >= 32L * 32 * 32 && !tma_disabled()) {
         const T* base = v.p - (long)v.halo * v.s2;
-        bool ok = ((uintptr_t)base % 16 == 0) && encode_map3<T>(&M.phi, base, v.n[0], v.n[1], (long)v.n[2] + 2L * v.halo, G::W, G::HH);
+        bool ok = ((uintptr_t)base % 16 == 0) && cached_map3<T>(&M.phi, base, v.n[0], v.n[1], (long)v.n[2] + 2L * v.halo, G::W, G::HH);
         for (int a = 0; ok && a < A.n; ++a)
-            ok = ((uintptr_t)A.src[a] % 16 == 0) && encode_map3<T>(&M.aux[a], A.src[a], v.n[0], v.n[1], v.n[2], TX, TY * NY);
+            ok = ((uintptr_t)A.src[a] % 16 == 0) && cached_map3<T>(&M.aux[a], A.src[a], v.n[0], v.n[1], v.n[2], TX, TY * NY);
         M.enabled = ok ? 1 : 0;
     }
     dim3 block(TX, TY), grid;
@@ -843,7 +602,7 @@ bool stage_tiled_supported(int ndim, const StageParams<T>& P) {
 }
 
 template <class T>
-cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, cudaStream_t s) {
+cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, cudaStream_t s, bool allow_pair, int* used_pair) {
     if (!stage_tiled_supported<T>(ndim, P)) return cudaErrorNotSupported;
     if (P.r1 <= P.r0) return cudaSuccess;
     AuxList A{};
@@ -860,6 +619,10 @@ cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, 
         }
     }
     if (P.p0) { A.p0 = A.n; A.src[A.n++] = P.p0; }
+    if (allow_pair && ndim == 3 && mask == M_ADV_WENO) {      // headline path: x-pair kernel (lsm_pair3d.cu); falls through when it does not apply
+        const cudaError_t e = launch_stage_pair3d<T>(P, A, s);
+        if (e != cudaErrorNotSupported) { if (used_pair) *used_pair = 1; return e; }
+    }
     bool remap = true;     // every BC an index map?  (ExtrapolationBC{P>=1} is a weighted stencil)
     for (int d = 0; d < ndim; ++d)
         for (int sd = 0; sd < 2; ++sd)
@@ -872,11 +635,11 @@ cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, 
 // instantiations build in parallel; without either macro both are instantiated here.
 #if !defined(LSM_TILED_F64)
 template bool stage_tiled_supported<float>(int, const StageParams<float>&);
-template cudaError_t launch_stage_tiled<float>(int, const StageParams<float>&, int, cudaStream_t);
+template cudaError_t launch_stage_tiled<float>(int, const StageParams<float>&, int, cudaStream_t, bool, int*);
 #endif
 #if !defined(LSM_TILED_F32)
 template bool stage_tiled_supported<double>(int, const StageParams<double>&);
-template cudaError_t launch_stage_tiled<double>(int, const StageParams<double>&, int, cudaStream_t);
+template cudaError_t launch_stage_tiled<double>(int, const StageParams<double>&, int, cudaStream_t, bool, int*);
 #endif
 
 }  // namespace lsm

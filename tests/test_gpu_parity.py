@@ -221,6 +221,81 @@ def test_config_parity_100_steps(m, O, name, mk, dtype):
     print(f"{name} {np.dtype(dtype).name}: {n} steps, max-abs diff {d:.3e}")
 
 
+# SURVEY.md §8(d) sizes: 128^3 (3-D) / 512^2 (2-D), 100 RK3 steps (C4: 50).  At these sizes interior tiles take the TMA ring
+# path of every kernel family, z marching spans several chunks per block column and the 3-blocks/SM instantiations are resident,
+# so the production kernels are compared with the oracle DIRECTLY (not through the strict kernel).  The observed max-abs
+# difference is printed for each case (-s / -rP shows it; profiles/parity_rNN.txt keeps a copy).
+CONFIGS_BIG = [
+    ("C2-512", lambda dt: H.c2_zalesak_curvature(512, dt)),
+    ("C3-128", lambda dt: H.c3_enright(128, dt)),
+    ("C3sep-128", lambda dt: H.c3_enright(128, dt, separable=True)),
+    ("C4-128", lambda dt: H.c4_eikonal(128, dt)),
+    ("C5-128", lambda dt: H.c5_normal_advection(128, dt)),
+]
+
+
+@pytest.mark.parametrize("name,mk", CONFIGS_BIG, ids=[c[0] for c in CONFIGS_BIG])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_config_parity_survey_sizes(m, O, name, mk, dtype):
+    case = mk(dtype)
+    steps = 50 if name.startswith("C4") else 100
+    O.set_threads(O.max_threads())
+    a, b, t, n = run_pair(m, O, case, integ="RK3", steps=steps)
+    assert n >= 0.9 * steps
+    d = check_parity(a, b, 1e-10 if dtype == np.float64 else 1e-4)
+    print(f"PARITY {name} {np.dtype(dtype).name}: {n} steps, max-abs diff {d:.3e} (bar {'1e-10' if dtype == np.float64 else '1e-4'})")
+
+
+def _pair_case(n, bc, dtype, separable):
+    lc, hc = (0, 0, 0), (1, 1, 1)
+    x, y, z = H.coords(lc, hc, n)
+    phi = np.sqrt((x - 0.35) ** 2 + (y - 0.4) ** 2 + (z - 0.45) ** 2) - 0.15 + 0.02 * np.sin(9 * x) * np.cos(7 * y) * np.sin(5 * z)
+    sc, tabs = H.enright_tables(lc, hc, n)
+    tabs = [[t + 0.05 * (a + 1) for a, t in enumerate(row)] for row in tabs]       # sign changes in every direction, no exact zeros
+    if separable:
+        term = dict(kind="advection", separable=(sc, tabs), cos_period=3.0)
+    else:
+        X, Y, Z = np.meshgrid(*[np.arange(k) for k in n], indexing="ij", sparse=True)
+        u = np.stack([((sc[d] * tabs[d][0][X]) * tabs[d][1][Y]) * tabs[d][2][Z] for d in range(3)], axis=0)
+        term = dict(kind="advection", field=u, cos_period=3.0)
+    return H.Case("P", lc, hc, n, phi, [term], bc, dtype)
+
+
+PAIR_SHAPES = [(128, 64, 40), (72, 52, 37), (64, 8, 8), (200, 30, 70), (136, 9, 130)]
+PAIR_BCS = [("neumann",), ("periodic",), ("symmetry",),
+            ((("neumann",), ("symmetry",)), ("periodic",), (("symmetry",), ("neumann",)))]
+
+
+@pytest.mark.parametrize("n", PAIR_SHAPES, ids=["x".join(map(str, s)) for s in PAIR_SHAPES])
+def test_pair_kernel_bitwise_vs_tiled(m, n):
+    """The x-pair kernel (csrc/lsm_pair3d.cu: TMA for every tile, lazy ghost fix-up, direction branches, shared differences)
+    performs the same operations as the general tiled kernel, so LSM_OPT_KERNEL = 0 and 3 must give BIT-IDENTICAL states:
+    partial tiles on every side, every index-map BC (also mixed per side), FE / RK2 / RK3, stored and separable velocity,
+    sign changes of the velocity inside warps and pairs, both dtypes."""
+    ctx = m.default_context()
+    k = 0
+    for bc in PAIR_BCS:
+        for dtype in (np.float64, np.float32):
+            if dtype == np.float32 and n[0] % 4:
+                continue
+            k += 1
+            case = _pair_case(n, bc, dtype, separable=(k % 3 == 0))
+            integ = (m.RK3, m.RK2, m.ForwardEuler)[k % 3]
+            outs = []
+            for kernel in (0, 3):
+                ctx.set_option(OPT_KERNEL, kernel)
+                ctx.reset_counters()
+                phi = case.engine_field(m)
+                eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=integ())
+                dt = 0.5 * m.compute_cfl(eq.terms, eq.state, 0.0)
+                m.integrate(eq, 3 * dt * (1 - 1e-12))
+                outs.append((eq.t, eq.steps_taken, eq.state.peek().copy(), ctx.counters()["pair_launches"]))
+            ctx.set_option(OPT_KERNEL, 0)
+            assert outs[0][3] > 0 and outs[1][3] == 0, "kernel selection"
+            assert outs[0][:2] == outs[1][:2]
+            assert np.array_equal(outs[0][2], outs[1][2]), (n, bc, np.dtype(dtype).name, float(np.abs(outs[0][2] - outs[1][2]).max()))
+
+
 def test_against_committed_vectors(m):
     """The engine against tests/golden/oracle_vectors.npz (committed oracle outputs for small instances of C1..C5, f64 and
     f32): catches a change that moves the oracle and the engine together."""
