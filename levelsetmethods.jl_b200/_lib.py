@@ -22,7 +22,7 @@ UPWIND, WENO5 = 0, 1
 COEF_CONST, COEF_FIELD, COEF_SEPARABLE, COEF_NONE = 0, 1, 2, 3
 TS_NONE, TS_COS, TS_HOST = 0, 1, 2
 FORWARD_EULER, RK2, RK3 = 0, 1, 2
-OPT_KERNEL, OPT_TIME_STAGES, OPT_CFL_CACHE, OPT_OVERLAP, OPT_FUSE_CFL, OPT_GRAPH = 0, 1, 2, 3, 4, 5
+OPT_KERNEL, OPT_TIME_STAGES, OPT_CFL_CACHE, OPT_OVERLAP, OPT_FUSE_CFL, OPT_GRAPH, OPT_CFL_CANDIDATES = 0, 1, 2, 3, 4, 5, 6
 MAX_TERMS = 4
 
 

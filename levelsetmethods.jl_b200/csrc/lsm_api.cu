@@ -51,6 +51,20 @@ inline double jl_eps(double x) {    // Base.eps(::Float64)
 
 struct CflCacheEntry { int kind; const void* field; uint64_t version; double g; int scaled; unsigned long long bits; };
 
+// Exact CFL maximum of a TIME-SCALED static coefficient field without touching the device again (replaces a per-step reduction
+// pass + 8-byte D2H + host sync).  The reference's per-node quantity is s_i(g) = sum_d fl(|fl(u_d g)| / h_d) (levelsetterms.jl:
+// 90-96) = |g| S_i (1 + theta), |theta| <= 4.5e-16, with S_i = sum_d |u_d| / h_d.  A node with S_i < (1 - 1e-12) max_j S_j can
+// therefore never attain max_i s_i(g) for ANY g, so the maximum over the (few) candidate nodes above that threshold, evaluated on
+// the host with the same IEEE operations, is bit-identical to the full reduction.  For the scalar coefficients (normal motion,
+// curvature) |fl(v g)| is monotone in |v|, and the same argument holds with S_i = |v_i|.
+struct CflCand {
+    int kind = 0; const void* field = nullptr; uint64_t version = 0;
+    int ncomp = 0, seen = 0;
+    bool built = false, overflow = false;
+    std::vector<double> tup;     // distinct raw coefficient tuples of the candidate nodes (all ranks)
+};
+constexpr int CAND_CAP = 8192;   // per rank
+
 }  // namespace
 
 struct lsm_ctx {
@@ -63,6 +77,9 @@ struct lsm_ctx {
     lsm_counters cnt{};
     int opt_kernel = 0, opt_time = 0, opt_cfl_cache = 1, opt_overlap = 1;
     std::vector<CflCacheEntry> cfl_cache;
+    std::vector<CflCand> cfl_cand;
+    int opt_cand = 1;           // LSM_OPT_CFL_CANDIDATES
+    unsigned* d_cand_count = nullptr; double* d_cand = nullptr; double* h_cand = nullptr;   // candidate staging (device / pinned)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;     // pending stage timings
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t ev_user[8] = {};
@@ -304,7 +321,7 @@ int32_t launch_stage_range(lsm_ctx* c, int ndim, StageParams<T>& P, int r0, int 
     P.r0 = r0; P.r1 = r1;
     cudaError_t e = cudaErrorNotSupported;
     int used_pair = 0;
-    if (c->opt_kernel != 1 && stage_tiled_supported<T>(ndim, P)) e = launch_stage_tiled<T>(ndim, P, c->sm_count, st, c->opt_kernel != 3, &used_pair);
+    if (c->opt_kernel != 1 && stage_tiled_supported<T>(ndim, P)) e = launch_stage_tiled<T>(ndim, P, c->sm_count, st, c->opt_kernel == 3 ? 0 : (c->opt_kernel == 4 ? 2 : 1), &used_pair);
     else if (c->opt_kernel == 2) return fail(LSM_ERR_UNSUPPORTED, "tiled kernel forced but this configuration is not covered");
     if (e == cudaErrorNotSupported) e = launch_stage_generic<T>(ndim, P, st);
     if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "stage kernel launch failed: %s", cudaGetErrorString(e));
@@ -424,6 +441,136 @@ int32_t stage_impl(lsm_ctx* ctx, int integ, int stage, lsm_field* phi, const lsm
 
 int nstages(int integ) { return integ == LSM_FORWARD_EULER ? 1 : integ == LSM_RK2 ? 2 : 3; }
 
+unsigned long long dbits(double s) {
+    unsigned long long b;
+    if (std::isnan(s)) return 0x7FF8000000000000ULL;
+    std::memcpy(&b, &s, 8);
+    return b;
+}
+
+// max over the candidate tuples of the reference's per-node CFL quantity at scale g — the expression of cfl_kernel, operation
+// for operation (this translation unit is compiled without FMA contraction)
+unsigned long long cand_eval(const CflCand& e, const lsm_field* phi, double g) {
+    unsigned long long best = 0ULL;
+    const size_t n = e.tup.size() / e.ncomp;
+    for (size_t k = 0; k < n; ++k) {
+        const double* v = &e.tup[k * e.ncomp];
+        double acc;
+        if (e.kind == LSM_TERM_ADVECTION) {
+            acc = 0.0;
+            for (int d = 0; d < e.ncomp; ++d) {
+                const double w = v[d] * g;
+                const double q = std::fabs(w) / phi->h[d];
+                acc = d == 0 ? q : acc + q;
+            }
+        } else {
+            acc = std::fabs(v[0] * g);
+        }
+        const unsigned long long b = dbits(acc);
+        best = b > best ? b : best;
+    }
+    return best;
+}
+
+CflCand* cand_find(lsm_ctx* ctx, const lsm_term& t) {
+    for (auto& e : ctx->cfl_cand) if (e.kind == t.kind && e.field == t.field) return &e;
+    return nullptr;
+}
+
+bool cand_ready(lsm_ctx* ctx, const lsm_term& t) {
+    if (!ctx->opt_cand || !ctx->opt_cfl_cache || !t.field) return false;
+    const CflCand* e = cand_find(ctx, t);
+    return e && e->built && !e->overflow && e->version == t.field->version;
+}
+
+int32_t raw_cfl_pass(lsm_ctx* ctx, lsm_field* phi, const TermDev& td, unsigned long long* bits_out) {
+    CflParams P{};
+    P.term = td;
+    for (int d = 0; d < 3; ++d) { P.n[d] = phi->n[d]; P.h[d] = phi->h[d]; }
+    P.out = ctx->d_scalar;
+    CU(cudaMemsetAsync(ctx->d_scalar, 0, 8, ctx->stream));
+    cudaError_t e = launch_cfl(phi->ndim, phi->dtype == LSM_F64, P, ctx->sm_count, ctx->stream);
+    if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "CFL kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->cnt.kernel_launches += 1; ctx->cnt.cfl_passes += 1;
+    if (ctx->nranks > 1) NC(nccl().AllReduce(ctx->d_scalar, ctx->d_scalar, 1, ncclUint64, ncclMax, ctx->nccl_comm, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_scalar, ctx->d_scalar, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->cnt.d2h_bytes += 8;
+    *bits_out = *ctx->h_scalar;
+    return LSM_OK;
+}
+
+// Build the candidate set of a scaled coefficient field: one unscaled reduction (global maximum M), one extraction pass
+// (nodes with S_i >= (1 - 1e-12) M), one gather.  Multi-rank: every rank contributes a fixed-size segment of a zero-filled
+// buffer and the segments are concatenated with an all-reduce(sum) (x + 0 = x exactly), so all ranks hold the same set.
+int32_t cand_build(lsm_ctx* ctx, lsm_field* phi, const lsm_term& t, const TermDev& td_scaled, CflCand* e) {
+    TermDev td = td_scaled;
+    td.scaled = 0; td.g = 1.0;
+    e->ncomp = t.kind == LSM_TERM_ADVECTION ? phi->ndim : 1;
+    e->built = false; e->overflow = false; e->tup.clear();
+    unsigned long long mb = 0;
+    TRY(raw_cfl_pass(ctx, phi, td, &mb));
+    double M; std::memcpy(&M, &mb, 8);
+    const int R = ctx->nranks;
+    const size_t seg = 1 + (size_t)CAND_CAP * e->ncomp;          // [count, tuples...] per rank
+    const size_t total = seg * R;
+    if (!ctx->d_cand) {
+        const size_t cap_bytes = (1 + (size_t)CAND_CAP * 3) * (size_t)R * sizeof(double);
+        CU(cudaMalloc(&ctx->d_cand, cap_bytes));
+        CU(cudaMalloc(&ctx->d_cand_count, 16));
+        CU(cudaMallocHost(&ctx->h_cand, cap_bytes));
+    }
+    if (M == 0.0) {                                              // identically zero field: s_i(g) = 0 for every g
+        e->tup.assign(e->ncomp, 0.0);
+        e->built = true;
+        return LSM_OK;
+    }
+    CandParams P{};
+    P.term = td;
+    for (int d = 0; d < 3; ++d) { P.n[d] = phi->n[d]; P.h[d] = phi->h[d]; }
+    P.thr = M * (1.0 - 1e-12);                                    // NaN maximum -> every node qualifies -> overflow -> regular path
+    P.cap = CAND_CAP; P.ncomp = e->ncomp;
+    P.count = ctx->d_cand_count;
+    P.out = ctx->d_cand + seg * ctx->rank + 1;
+    CU(cudaMemsetAsync(ctx->d_cand, 0, total * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_cand_count, 0, 4, ctx->stream));
+    cudaError_t ce = launch_cfl_candidates(phi->ndim, phi->dtype == LSM_F64, P, ctx->sm_count, ctx->stream);
+    if (ce != cudaSuccess) return fail(LSM_ERR_CUDA, "CFL candidate kernel launch failed: %s", cudaGetErrorString(ce));
+    ctx->cnt.kernel_launches += 1;
+    unsigned cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, ctx->d_cand_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const double cntd = (double)cnt;
+    CU(cudaMemcpyAsync(ctx->d_cand + seg * ctx->rank, &cntd, 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (R > 1) NC(nccl().AllReduce(ctx->d_cand, ctx->d_cand, total, ncclDouble, ncclSum, ctx->nccl_comm, ctx->stream));
+    // single rank: only the filled part of the segment travels
+    const size_t take = R > 1 ? total : 1 + (size_t)std::min<unsigned>(cnt, (unsigned)CAND_CAP) * e->ncomp;
+    CU(cudaMemcpyAsync(ctx->h_cand, ctx->d_cand, take * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->cnt.d2h_bytes += (int64_t)(take * sizeof(double)) + 4;
+    std::vector<std::vector<double>> rows;
+    for (int r = 0; r < R; ++r) {
+        const double* sg = ctx->h_cand + seg * r;
+        const double c = sg[0];
+        if (!(c <= (double)CAND_CAP)) { e->overflow = true; return LSM_OK; }      // too many ties (e.g. a constant field): regular path
+        for (int k = 0; k < (int)c; ++k) rows.emplace_back(sg + 1 + (size_t)k * e->ncomp, sg + 1 + (size_t)(k + 1) * e->ncomp);
+    }
+    if (rows.empty()) { e->overflow = true; return LSM_OK; }                       // cannot happen (the maximum itself qualifies)
+    // distinct tuples only (NaN-safe: compare bit patterns)
+    auto key = [](const std::vector<double>& a, const std::vector<double>& b) {
+        for (size_t i = 0; i < a.size(); ++i) {
+            unsigned long long x, y; std::memcpy(&x, &a[i], 8); std::memcpy(&y, &b[i], 8);
+            if (x != y) return x < y;
+        }
+        return false;
+    };
+    std::sort(rows.begin(), rows.end(), key);
+    for (size_t i = 0; i < rows.size(); ++i)
+        if (i == 0 || key(rows[i - 1], rows[i])) e->tup.insert(e->tup.end(), rows[i].begin(), rows[i].end());
+    e->built = true;
+    return LSM_OK;
+}
+
 // max over owned nodes of the CFL quantity of one term, as IEEE bits (see lsm_generic.cu K3)
 int32_t cfl_bits(lsm_ctx* ctx, lsm_field* phi, const lsm_term& t, double g, unsigned long long* bits_out) {
     TermDev td;
@@ -432,6 +579,16 @@ int32_t cfl_bits(lsm_ctx* ctx, lsm_field* phi, const lsm_term& t, double g, unsi
         for (const auto& e : ctx->cfl_cache)
             if (e.kind == t.kind && e.field == t.field && e.version == t.field->version && e.scaled == td.scaled &&
                 (!td.scaled || e.g == g)) { *bits_out = e.bits; return LSM_OK; }
+    }
+    if (ctx->opt_cand && ctx->opt_cfl_cache && td.scaled && (t.coef_kind == LSM_COEF_FIELD || t.coef_kind == LSM_COEF_SEPARABLE)) {
+        // time-scaled static coefficient: the second request for the same data builds the candidate set, every later one is
+        // answered on the host (no kernel, no D2H, no sync)
+        CflCand* e = cand_find(ctx, t);
+        if (!e) { ctx->cfl_cand.emplace_back(); e = &ctx->cfl_cand.back(); e->kind = t.kind; e->field = t.field; e->version = ~0ULL; }
+        if (e->version != t.field->version) { e->version = t.field->version; e->seen = 0; e->built = false; e->overflow = false; e->tup.clear(); }
+        e->seen++;
+        if (!e->built && !e->overflow && e->seen >= 2) { ctx->fused.valid = false; TRY(cand_build(ctx, phi, t, td, e)); }
+        if (e->built && !e->overflow) { *bits_out = cand_eval(*e, phi, g); return LSM_OK; }
     }
     if (ctx->fused.valid) {
         ctx->fused.valid = false;
@@ -590,6 +747,9 @@ int32_t lsm_ctx_destroy(lsm_ctx* c) {
     if (c->nccl_comm) nccl().CommDestroy(c->nccl_comm);
     if (c->d_scalar) cudaFree(c->d_scalar);
     if (c->h_scalar) cudaFreeHost(c->h_scalar);
+    if (c->d_cand) cudaFree(c->d_cand);
+    if (c->d_cand_count) cudaFree(c->d_cand_count);
+    if (c->h_cand) cudaFreeHost(c->h_cand);
     if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
@@ -611,9 +771,10 @@ int32_t lsm_sync(lsm_ctx* c) {
 int32_t lsm_set_option(lsm_ctx* c, int32_t option, int32_t value) {
     if (!c) return fail(LSM_ERR_ARG, "null context");
     switch (option) {
-        case LSM_OPT_KERNEL: if (value < 0 || value > 3) return fail(LSM_ERR_ARG, "LSM_OPT_KERNEL takes 0, 1, 2 or 3"); c->opt_kernel = value; break;
+        case LSM_OPT_KERNEL: if (value < 0 || value > 4) return fail(LSM_ERR_ARG, "LSM_OPT_KERNEL takes 0..4"); c->opt_kernel = value; break;
         case LSM_OPT_TIME_STAGES: c->opt_time = value != 0; break;
-        case LSM_OPT_CFL_CACHE: c->opt_cfl_cache = value != 0; c->cfl_cache.clear(); break;
+        case LSM_OPT_CFL_CACHE: c->opt_cfl_cache = value != 0; c->cfl_cache.clear(); c->cfl_cand.clear(); break;
+        case LSM_OPT_CFL_CANDIDATES: c->opt_cand = value != 0; c->cfl_cand.clear(); break;
         case LSM_OPT_OVERLAP: c->opt_overlap = value != 0; break;
         case LSM_OPT_FUSE_CFL: c->opt_fuse_cfl = value != 0; break;
         case LSM_OPT_GRAPH: c->opt_graph = value != 0; break;
@@ -724,6 +885,9 @@ int32_t lsm_field_destroy(lsm_field* f) {
     // drop CFL cache entries that point at this field
     auto& cc = f->ctx->cfl_cache;
     for (size_t i = 0; i < cc.size();) { if (cc[i].field == f) cc.erase(cc.begin() + i); else ++i; }
+    auto& cd = f->ctx->cfl_cand;
+    for (size_t i = 0; i < cd.size();) { if (cd[i].field == f) cd.erase(cd.begin() + i); else ++i; }
+    if (f->ctx->fused.field == f) f->ctx->fused.valid = false;       // a new field at the same address must not consume a stale fused maximum
     field_free(f);
     return LSM_OK;
 }
@@ -926,7 +1090,8 @@ int32_t lsm_integrate(lsm_ctx* ctx, int32_t integrator, double cfl, lsm_field* p
         const bool capturing = capture && graph_ok;
         for (int s = 1; s <= nstages(integrator) && rc == LSM_OK; ++s) {
             if (s == nstages(integrator) && ctx->opt_fuse_cfl && ctx->opt_cfl_cache && nterms == 1 && terms[0].kind == LSM_TERM_ADVECTION &&
-                (terms[0].coef_kind == LSM_COEF_FIELD || terms[0].coef_kind == LSM_COEF_SEPARABLE) && terms[0].tscale_kind == LSM_TS_COS && (tc + dt) <= tf - jl_eps(tc + dt)) {
+                (terms[0].coef_kind == LSM_COEF_FIELD || terms[0].coef_kind == LSM_COEF_SEPARABLE) && terms[0].tscale_kind == LSM_TS_COS && (tc + dt) <= tf - jl_eps(tc + dt) &&
+                !(ctx->opt_cand && cand_find(ctx, terms[0]) && !cand_find(ctx, terms[0])->overflow && cand_find(ctx, terms[0])->version == terms[0].field->version)) {
                 // next step's CFL maximum from this stage's velocity traffic: max(g') >= (1 - 1e-13) * max(g) * |g'/g|
                 for (const auto& en : ctx->cfl_cache)
                     if (en.kind == terms[0].kind && en.field == terms[0].field && en.version == terms[0].field->version && en.scaled && en.g != 0.0) {

@@ -436,6 +436,55 @@ cudaError_t launch_cfl(int ndim, int dtype_f64, const CflParams& P, int sm_count
     return cudaGetLastError();
 }
 
+// Candidate nodes of the CFL maximum (lsm_api.cu, cfl_candidates): the unscaled quantity s = sum_d |u_d| / h_d (advection) or
+// |v| (normal motion, curvature), formed exactly like cfl_kernel does with g = 1; nodes with !(s < thr) — NaN included —
+// append their raw coefficient tuple.
+template <int N, class T>
+__global__ void __launch_bounds__(256) cfl_candidates_kernel(const __grid_constant__ CandParams P) {
+    const TermDev& t = P.term;
+    const long total = (long)P.n[0] * P.n[1] * P.n[2];
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int i0 = (int)(idx % P.n[0]);
+        const long q = idx / P.n[0];
+        const int i1 = (int)(q % P.n[1]);
+        const int i2 = (int)(q / P.n[1]);
+        double v[3] = {0.0, 0.0, 0.0};
+        double s;
+        if (t.kind == TERM_ADVECTION) {
+            s = 0.0;
+#pragma unroll
+            for (int d = 0; d < N; ++d) {
+                v[d] = coef_comp<T>(t, idx, d, i0, i1, i2, N);
+                const double q2 = fabs(v[d]) / P.h[d];
+                s = (d == 0) ? q2 : s + q2;
+            }
+        } else {
+            v[0] = coef_comp<T>(t, idx, 0, i0, i1, i2, N);
+            s = fabs(v[0]);
+        }
+        if (!(s < P.thr)) {
+            const unsigned k = atomicAdd(P.count, 1u);
+            if (k < (unsigned)P.cap)
+                for (int d = 0; d < P.ncomp; ++d) P.out[(long)k * P.ncomp + d] = v[d];
+        }
+    }
+}
+
+cudaError_t launch_cfl_candidates(int ndim, int dtype_f64, const CandParams& P, int sm_count, cudaStream_t s) {
+    const long total = (long)P.n[0] * P.n[1] * P.n[2];
+    const int block = 256;
+    long grid = (total + block - 1) / block;
+    const long cap = (long)sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+#define LSM_CAND(NN) do { if (dtype_f64) cfl_candidates_kernel<NN, double><<<(unsigned)grid, block, 0, s>>>(P); \
+                          else cfl_candidates_kernel<NN, float><<<(unsigned)grid, block, 0, s>>>(P); } while (0)
+    if (ndim == 1) LSM_CAND(1); else if (ndim == 2) LSM_CAND(2); else LSM_CAND(3);
+#undef LSM_CAND
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // small elementwise kernels
 // ---------------------------------------------------------------------------------------------

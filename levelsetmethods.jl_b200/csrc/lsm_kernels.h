@@ -11,9 +11,22 @@ struct CflParams {
     unsigned long long* out;   // device scalar, zeroed by the caller
 };
 
+// CFL candidate extraction (see lsm_api.cu, cfl_candidates): every node whose unscaled CFL quantity reaches `thr` appends its
+// raw coefficient tuple (ncomp doubles) to `out`; `count` keeps counting past `cap` so that the host can tell an overflow.
+struct CandParams {
+    TermDev term;              // scaled == 0
+    int n[3];
+    double h[3];
+    double thr;
+    int cap, ncomp;
+    unsigned* count;           // device counter, zeroed by the caller
+    double* out;               // cap x ncomp
+};
+
 // lsm_generic.cu (strict arithmetic, -fmad=false)
 template <class T> cudaError_t launch_stage_generic(int ndim, const StageParams<T>& P, cudaStream_t s);
 cudaError_t launch_cfl(int ndim, int dtype_f64, const CflParams& P, int sm_count, cudaStream_t s);
+cudaError_t launch_cfl_candidates(int ndim, int dtype_f64, const CandParams& P, int sm_count, cudaStream_t s);
 cudaError_t launch_eikonal_s0(int src_f64, int dst_f64, const void* phi, void* out, long n, double dx, cudaStream_t s);
 cudaError_t launch_transpose(int f64, bool to_soa, const void* src, void* dst, long n, int ncomp, long cstride, cudaStream_t s);
 template <class T> cudaError_t launch_getindex(int ndim, const View<T>& v, const int* d_idx, int count, double* d_out, cudaStream_t s);
@@ -37,11 +50,11 @@ struct AuxList {
 };
 
 // lsm_pair3d.cu (3-D single-term WENO5 advection, x-pair threads).  cudaErrorNotSupported -> use the general tiled kernel.
-template <class T> cudaError_t launch_stage_pair3d(const StageParams<T>& P, const AuxList& A, cudaStream_t s);
+template <class T> cudaError_t launch_stage_pair3d(const StageParams<T>& P, const AuxList& A, cudaStream_t s, bool exact_eps);
 
 // lsm_tiled.cu (performance kernels).  Returns cudaErrorNotSupported when the configuration is
 // not covered, in which case the caller uses the generic kernel.
-template <class T> cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, cudaStream_t s, bool allow_pair = true, int* used_pair = nullptr);
+template <class T> cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, cudaStream_t s, int pair_mode = 1, int* used_pair = nullptr);   // pair_mode: 0 never, 1 x-pair kernel (20-bit eps max), 2 x-pair kernel with the exact eps max
 template <class T> bool stage_tiled_supported(int ndim, const StageParams<T>& P);
 
 }  // namespace lsm

@@ -63,13 +63,11 @@ struct PairGeom {
 // weno5_up of lsm_tile_util.cuh (second differences, one reciprocal); returns h * weno.  The function is odd:
 // core(-v5..-v1 reversed) == -core(...) bit for bit, which is what makes the physical-order evaluation below
 // identical to the upwind-ordered one of lsm_tiled.cu.
-template <class T>
-__device__ __forceinline__ double weno_core(const WenoK& K, T v1, T v2, T v3, T v4, T v5);
-
-template <>
-__device__ __forceinline__ double weno_core<double>(const WenoK& K, double d0, double d1, double d2, double d3, double d4) {
+// XMAX: exact max|d| for eps (bit-identical to lsm_tiled.cu) instead of the 20-bit one (absmax5_hi).
+template <bool XMAX>
+__device__ __forceinline__ double weno_core(const WenoK& K, double d0, double d1, double d2, double d3, double d4) {
     const double e1 = d1 - d0, e2 = d2 - d1, e3 = d3 - d2, e4 = d4 - d3;
-    const double m = absmax5_hi(d0, d1, d2, d3, d4);
+    const double m = XMAX ? absmax5(d0, d1, d2, d3, d4) : absmax5_hi(d0, d1, d2, d3, d4);
     const double eps = fma(K.e6, m * m, K.fl);
     const double c133 = K.c133;
     const double t1a = e2 - e1, t1b = e3 - e2, t1c = e4 - e3;
@@ -88,8 +86,8 @@ __device__ __forceinline__ double weno_core<double>(const WenoK& K, double d0, d
 }
 
 // Float32 fields: all-FP32 evaluation with the differences normalised by 1/max|d| (see weno5_up<float>)
-template <>
-__device__ __forceinline__ double weno_core<float>(const WenoK&, float d0, float d1, float d2, float d3, float d4) {
+template <bool XMAX>
+__device__ __forceinline__ double weno_core(const WenoK&, float d0, float d1, float d2, float d3, float d4) {
     const float e1 = d1 - d0, e2 = d2 - d1, e3 = d3 - d2, e4 = d4 - d3;
     const float m = fmaxf(fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fmaxf(fabsf(d2), fabsf(d3))), fabsf(d4));
     const float im = m > 0.f ? __frcp_rn(m) : 0.f;
@@ -114,21 +112,21 @@ __device__ __forceinline__ double weno_core<float>(const WenoK&, float d0, float
 // node A / B; xa / xb carries sign(u * g) of the node in bit 31 (set: plus-biased stencil, derivatives.jl:109-121; clear:
 // minus-biased, :89-101).  When B is A's neighbour along the dimension the caller passes b[k] = a[k + 1] and the common
 // differences are shared by the compiler's value numbering.
-template <class T>
+template <class T, bool XMAX>
 __device__ __forceinline__ void pair_eval(const WenoK& K, const T (&a)[7], const T (&b)[7], int xa, int xb, double& WA, double& WB) {
     if ((xa | xb) >= 0) {                 // both minus-biased: D-(I-2 .. I+2) = first differences -3 .. 1
-        WA = weno_core<T>(K, T(a[1] - a[0]), T(a[2] - a[1]), T(a[3] - a[2]), T(a[4] - a[3]), T(a[5] - a[4]));
-        WB = weno_core<T>(K, T(b[1] - b[0]), T(b[2] - b[1]), T(b[3] - b[2]), T(b[4] - b[3]), T(b[5] - b[4]));
+        WA = weno_core<XMAX>(K, T(a[1] - a[0]), T(a[2] - a[1]), T(a[3] - a[2]), T(a[4] - a[3]), T(a[5] - a[4]));
+        WB = weno_core<XMAX>(K, T(b[1] - b[0]), T(b[2] - b[1]), T(b[3] - b[2]), T(b[4] - b[3]), T(b[5] - b[4]));
     } else if ((xa & xb) < 0) {           // both plus-biased: D+(I+2), D+(I+1), D+(I), D+(I-1), D+(I-2)
-        WA = weno_core<T>(K, T(a[6] - a[5]), T(a[5] - a[4]), T(a[4] - a[3]), T(a[3] - a[2]), T(a[2] - a[1]));
-        WB = weno_core<T>(K, T(b[6] - b[5]), T(b[5] - b[4]), T(b[4] - b[3]), T(b[3] - b[2]), T(b[2] - b[1]));
+        WA = weno_core<XMAX>(K, T(a[6] - a[5]), T(a[5] - a[4]), T(a[4] - a[3]), T(a[3] - a[2]), T(a[2] - a[1]));
+        WB = weno_core<XMAX>(K, T(b[6] - b[5]), T(b[5] - b[4]), T(b[4] - b[3]), T(b[3] - b[2]), T(b[2] - b[1]));
     } else {                              // a sign change inside the pair: upwind-ordered samples per node (odd symmetry of the evaluation)
         const bool ma = xa >= 0, mb = xb >= 0;
         T qa[6], qb[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) { qa[k] = ma ? a[k] : a[6 - k]; qb[k] = mb ? b[k] : b[6 - k]; }
-        const double wa = weno_core<T>(K, T(qa[1] - qa[0]), T(qa[2] - qa[1]), T(qa[3] - qa[2]), T(qa[4] - qa[3]), T(qa[5] - qa[4]));
-        const double wb = weno_core<T>(K, T(qb[1] - qb[0]), T(qb[2] - qb[1]), T(qb[3] - qb[2]), T(qb[4] - qb[3]), T(qb[5] - qb[4]));
+        const double wa = weno_core<XMAX>(K, T(qa[1] - qa[0]), T(qa[2] - qa[1]), T(qa[3] - qa[2]), T(qa[4] - qa[3]), T(qa[5] - qa[4]));
+        const double wb = weno_core<XMAX>(K, T(qb[1] - qb[0]), T(qb[2] - qb[1]), T(qb[3] - qb[2]), T(qb[4] - qb[3]), T(qb[5] - qb[4]));
         WA = ma ? wa : -wa;
         WB = mb ? wb : -wb;
     }
@@ -136,7 +134,7 @@ __device__ __forceinline__ void pair_eval(const WenoK& K, const T (&a)[7], const
 
 // CK: COEF_FIELD (stored velocity, staged by TMA next to the phi ring) or COEF_SEPARABLE (u_d = s_d X_d[i] Y_d[j] Z_d[k] from tables).
 // SB: static RK base mode (SB_* of lsm_tile_util.cuh).  FCFL: also reduce the next step's CFL maximum (see StageParams).
-template <class T, int RY, int NT, int CK, bool FCFL, int SB>
+template <class T, int RY, int NT, int CK, bool FCFL, int SB, bool ISO, bool XMAX>
 __global__ void __launch_bounds__(NT, 2)
 pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ AuxList A, const __grid_constant__ TmaMaps M, const int cz) {
     using G = PairGeom<T, RY, NT>;
@@ -228,6 +226,11 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
     const double g = P.terms[0].scaled ? P.terms[0].g : 1.0;
     const int ghi = __double2hiint(g);
     const double gih[3] = {g * (1.0 / P.h[0]), g * (1.0 / P.h[1]), g * (1.0 / P.h[2])};
+    // ISO (equal mesh size in the three dimensions, the usual case): sum_d (u_d g / h) W_d = (g / h) sum_d u_d W_d, so the per-
+    // dimension scaling (3 DMUL per node) folds into the stage coefficient: x -= (c g / h) * sum_d u_d W_d.
+    const double tau = ISO ? P.cfl_tau / fabs(gih[0]) * (1.0 - 1e-15) : P.cfl_tau;      // candidate bound on the unscaled estimate (ISO)
+    const double cH = ISO ? P.c * gih[0] : P.c, cH2 = ISO ? P.c2 * gih[0] : P.c2;
+    auto scl = [&](double u, int d) -> double { return ISO ? u : u * gih[d]; };
     // separable velocity: the x-y factor of every node is a loop invariant (same product order as the stored tables)
     double pxy[RY][2][3];
     if (CK == COEF_SEPARABLE) {
@@ -307,9 +310,9 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
                 } else { ua = pxy[r][0][0] * __ldg(P.terms[0].tab[0][2] + z); ub = pxy[r][1][0] * __ldg(P.terms[0].tab[0][2] + z); }
                 uraw[r][0][0] = ua; uraw[r][1][0] = ub;
                 double wa, wb;
-                pair_eval<T>(KR, a, b, __double2hiint(ua) ^ ghi, __double2hiint(ub) ^ ghi, wa, wb);
-                H[r][0] = (ua * gih[0]) * wa;
-                H[r][1] = (ub * gih[0]) * wb;
+                pair_eval<T, XMAX>(KR, a, b, __double2hiint(ua) ^ ghi, __double2hiint(ub) ^ ghi, wa, wb);
+                H[r][0] = scl(ua, 0) * wa;
+                H[r][1] = scl(ub, 0) * wb;
             }
             // ---- y
             {
@@ -329,9 +332,9 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
                     const T a[7] = {yv[0].x, yv[1].x, yv[2].x, yv[3].x, yv[4].x, yv[5].x, yv[6].x};
                     const T b[7] = {yv[0].y, yv[1].y, yv[2].y, yv[3].y, yv[4].y, yv[5].y, yv[6].y};
                     double wa, wb;
-                    pair_eval<T>(KR, a, b, __double2hiint(u[0][0]) ^ ghi, __double2hiint(u[0][1]) ^ ghi, wa, wb);
-                    H[0][0] = fma(u[0][0] * gih[1], wa, H[0][0]);
-                    H[0][1] = fma(u[0][1] * gih[1], wb, H[0][1]);
+                    pair_eval<T, XMAX>(KR, a, b, __double2hiint(u[0][0]) ^ ghi, __double2hiint(u[0][1]) ^ ghi, wa, wb);
+                    H[0][0] = fma(scl(u[0][0], 1), wa, H[0][0]);
+                    H[0][1] = fma(scl(u[0][1], 1), wb, H[0][1]);
                 } else {
                     // rows j0, j0+1 of the same column share their samples
                     const T a0[7] = {yv[0].x, yv[1].x, yv[2].x, yv[3].x, yv[4].x, yv[5].x, yv[6].x};
@@ -339,12 +342,12 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
                     const T b0[7] = {yv[0].y, yv[1].y, yv[2].y, yv[3].y, yv[4].y, yv[5].y, yv[6].y};
                     const T b1[7] = {yv[1].y, yv[2].y, yv[3].y, yv[4].y, yv[5].y, yv[6].y, yv[6 + RY - 1].y};
                     double w00, w10, w01, w11;
-                    pair_eval<T>(KR, a0, a1, __double2hiint(u[0][0]) ^ ghi, __double2hiint(u[RY - 1][0]) ^ ghi, w00, w10);
-                    pair_eval<T>(KR, b0, b1, __double2hiint(u[0][1]) ^ ghi, __double2hiint(u[RY - 1][1]) ^ ghi, w01, w11);
-                    H[0][0] = fma(u[0][0] * gih[1], w00, H[0][0]);
-                    H[0][1] = fma(u[0][1] * gih[1], w01, H[0][1]);
-                    H[RY - 1][0] = fma(u[RY - 1][0] * gih[1], w10, H[RY - 1][0]);
-                    H[RY - 1][1] = fma(u[RY - 1][1] * gih[1], w11, H[RY - 1][1]);
+                    pair_eval<T, XMAX>(KR, a0, a1, __double2hiint(u[0][0]) ^ ghi, __double2hiint(u[RY - 1][0]) ^ ghi, w00, w10);
+                    pair_eval<T, XMAX>(KR, b0, b1, __double2hiint(u[0][1]) ^ ghi, __double2hiint(u[RY - 1][1]) ^ ghi, w01, w11);
+                    H[0][0] = fma(scl(u[0][0], 1), w00, H[0][0]);
+                    H[0][1] = fma(scl(u[0][1], 1), w01, H[0][1]);
+                    H[RY - 1][0] = fma(scl(u[RY - 1][0], 1), w10, H[RY - 1][0]);
+                    H[RY - 1][1] = fma(scl(u[RY - 1][1], 1), w11, H[RY - 1][1]);
                 }
             }
             // ---- z: the column of every node through the ring
@@ -362,9 +365,9 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
                 } else { ua = pxy[r][0][2] * __ldg(P.terms[0].tab[2][2] + z); ub = pxy[r][1][2] * __ldg(P.terms[0].tab[2][2] + z); }
                 uraw[r][0][2] = ua; uraw[r][1][2] = ub;
                 double wa, wb;
-                pair_eval<T>(KR, a, b, __double2hiint(ua) ^ ghi, __double2hiint(ub) ^ ghi, wa, wb);
-                H[r][0] = fma(ua * gih[2], wa, H[r][0]);
-                H[r][1] = fma(ub * gih[2], wb, H[r][1]);
+                pair_eval<T, XMAX>(KR, a, b, __double2hiint(ua) ^ ghi, __double2hiint(ub) ^ ghi, wa, wb);
+                H[r][0] = fma(scl(ua, 2), wa, H[r][0]);
+                H[r][1] = fma(scl(ub, 2), wb, H[r][1]);
             }
             // ---- RK stage combination (timestepping.jl:128-202) and the pair store
 #pragma unroll
@@ -382,13 +385,13 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
                     }
                 }
                 V2 o;
-                o.x = T(fma(-P.c, H[r][0], double(xb[0])));
-                o.y = T(fma(-P.c, H[r][1], double(xb[1])));
+                o.x = T(fma(-cH, H[r][0], double(xb[0])));
+                o.y = T(fma(-cH, H[r][1], double(xb[1])));
                 *reinterpret_cast<V2*>(P.out + lin + r * vs1) = o;
                 if (HAS_OUT2) {
                     V2 o2;
-                    o2.x = T(fma(-P.c2, H[r][0], double(cc[r].x)));
-                    o2.y = T(fma(-P.c2, H[r][1], double(cc[r].y)));
+                    o2.x = T(fma(-cH2, H[r][0], double(cc[r].x)));
+                    o2.y = T(fma(-cH2, H[r][1], double(cc[r].y)));
                     *reinterpret_cast<V2*>(P.out2 + lin + r * vs1) = o2;
                 }
                 if (FCFL) {
@@ -396,8 +399,9 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
                     for (int c = 0; c < 2; ++c) {
                         // cheap estimate sum_d |u_d| |g_stage| / h_d against the candidate bound; candidates evaluate the reference
                         // expression bit for bit (levelsetterms.jl:90-96)
-                        const double sest = (fabs(uraw[r][c][0] * gih[0]) + fabs(uraw[r][c][1] * gih[1])) + fabs(uraw[r][c][2] * gih[2]);
-                        if (!(sest < P.cfl_tau)) {
+                        const double sest = ISO ? (fabs(uraw[r][c][0]) + fabs(uraw[r][c][1])) + fabs(uraw[r][c][2])
+                                                : (fabs(uraw[r][c][0] * gih[0]) + fabs(uraw[r][c][1] * gih[1])) + fabs(uraw[r][c][2] * gih[2]);
+                        if (!(sest < tau)) {
                             double sx = 0.0;
 #pragma unroll
                             for (int d = 0; d < 3; ++d) {
@@ -444,11 +448,11 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
 #define LSM_PAIR_NT 256
 #endif
 
-template <class T, int CK, bool FCFL, int SB>
-cudaError_t launch_pair(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
+template <class T, int CK, bool FCFL, int SB, bool ISO, bool XMAX>
+cudaError_t launch_pair_x(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
     constexpr int RY = LSM_PAIR_RY, NT = LSM_PAIR_NT;
     using G = PairGeom<T, RY, NT>;
-    auto kern = pair3d_kernel<T, RY, NT, CK, FCFL, SB>;
+    auto kern = pair3d_kernel<T, RY, NT, CK, FCFL, SB, ISO, XMAX>;
     constexpr bool HAS_P0 = SB == SB_S2 || SB == SB_S3 || SB == SB_P0;
     constexpr int NAUX = (CK == COEF_FIELD ? 3 : 0) + (HAS_P0 ? 1 : 0);
     const size_t smem = G::smem_bytes(NAUX);
@@ -468,17 +472,27 @@ cudaError_t launch_pair(const StageParams<T>& P, const AuxList& A, cudaStream_t 
     return cudaGetLastError();
 }
 
+template <class T, int CK, bool FCFL, int SB>
+cudaError_t launch_pair(const StageParams<T>& P, const AuxList& A, cudaStream_t s, bool exact_eps) {
+    const bool iso = P.h[0] == P.h[1] && P.h[1] == P.h[2];
+    if (sizeof(T) == 4 || !exact_eps)      // (the Float32 evaluation normalises by the exact FP32 maximum either way)
+        return iso ? launch_pair_x<T, CK, FCFL, SB, true, false>(P, A, s) : launch_pair_x<T, CK, FCFL, SB, false, false>(P, A, s);
+    if constexpr (sizeof(T) == 8)
+        return iso ? launch_pair_x<T, CK, FCFL, SB, true, true>(P, A, s) : launch_pair_x<T, CK, FCFL, SB, false, true>(P, A, s);
+    return cudaErrorNotSupported;
+}
+
 template <class T, int CK, bool FCFL>
-cudaError_t launch_pair_sb(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
+cudaError_t launch_pair_sb(const StageParams<T>& P, const AuxList& A, cudaStream_t s, bool exact_eps) {
     constexpr int SP0 = CK == COEF_FIELD ? 3 : 0;
     if (A.p0 >= 0 && A.p0 != SP0) return cudaErrorNotSupported;
     if (P.base == BASE_IN && !P.p0) {
-        if (!P.out2) return launch_pair<T, CK, FCFL, SB_IN>(P, A, s);
-        if (!FCFL) return launch_pair<T, CK, false, SB_IN_OUT2>(P, A, s);
+        if (!P.out2) return launch_pair<T, CK, FCFL, SB_IN>(P, A, s, exact_eps);
+        if (!FCFL) return launch_pair<T, CK, false, SB_IN_OUT2>(P, A, s, exact_eps);
     }
-    if (P.base == BASE_RK3_S2 && P.p0 && !P.out2 && !FCFL) return launch_pair<T, CK, false, SB_S2>(P, A, s);
-    if (P.base == BASE_RK3_S3 && P.p0 && !P.out2) return launch_pair<T, CK, FCFL, SB_S3>(P, A, s);
-    if (P.base == BASE_P0 && P.p0 && !P.out2) return launch_pair<T, CK, FCFL, SB_P0>(P, A, s);
+    if (P.base == BASE_RK3_S2 && P.p0 && !P.out2 && !FCFL) return launch_pair<T, CK, false, SB_S2>(P, A, s, exact_eps);
+    if (P.base == BASE_RK3_S3 && P.p0 && !P.out2) return launch_pair<T, CK, FCFL, SB_S3>(P, A, s, exact_eps);
+    if (P.base == BASE_P0 && P.p0 && !P.out2) return launch_pair<T, CK, FCFL, SB_P0>(P, A, s, exact_eps);
     return cudaErrorNotSupported;
 }
 
@@ -487,7 +501,7 @@ cudaError_t launch_pair_sb(const StageParams<T>& P, const AuxList& A, cudaStream
 // Single-term 3-D WENO5 advection with index-map boundary conditions on a TMA-compatible box; anything else reports
 // cudaErrorNotSupported and the caller takes the general tiled kernel.
 template <class T>
-cudaError_t launch_stage_pair3d(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
+cudaError_t launch_stage_pair3d(const StageParams<T>& P, const AuxList& A, cudaStream_t s, bool exact_eps) {
     if (pair_kernel_disabled() || tma_disabled() || !encode_tiled_fn()) return cudaErrorNotSupported;
     if (P.nterms != 1) return cudaErrorNotSupported;
     const TermDev& t0 = P.terms[0];
@@ -502,13 +516,13 @@ cudaError_t launch_stage_pair3d(const StageParams<T>& P, const AuxList& A, cudaS
             if (!index_map) return cudaErrorNotSupported;
         }
     if (t0.coef_kind == COEF_FIELD && A.first[0] == 0 && !t0.coef_f64)
-        return P.cfl_out ? launch_pair_sb<T, COEF_FIELD, true>(P, A, s) : launch_pair_sb<T, COEF_FIELD, false>(P, A, s);
+        return P.cfl_out ? launch_pair_sb<T, COEF_FIELD, true>(P, A, s, exact_eps) : launch_pair_sb<T, COEF_FIELD, false>(P, A, s, exact_eps);
     if (t0.coef_kind == COEF_SEPARABLE)
-        return P.cfl_out ? launch_pair_sb<T, COEF_SEPARABLE, true>(P, A, s) : launch_pair_sb<T, COEF_SEPARABLE, false>(P, A, s);
+        return P.cfl_out ? launch_pair_sb<T, COEF_SEPARABLE, true>(P, A, s, exact_eps) : launch_pair_sb<T, COEF_SEPARABLE, false>(P, A, s, exact_eps);
     return cudaErrorNotSupported;
 }
 
-template cudaError_t launch_stage_pair3d<float>(const StageParams<float>&, const AuxList&, cudaStream_t);
-template cudaError_t launch_stage_pair3d<double>(const StageParams<double>&, const AuxList&, cudaStream_t);
+template cudaError_t launch_stage_pair3d<float>(const StageParams<float>&, const AuxList&, cudaStream_t, bool);
+template cudaError_t launch_stage_pair3d<double>(const StageParams<double>&, const AuxList&, cudaStream_t, bool);
 
 }  // namespace lsm

@@ -84,16 +84,21 @@ __device__ __forceinline__ double absmax5(double a, double b, double c, double d
     return m;
 }
 
-// max|a..e| to 21 significant bits: the largest high word (sign cleared) with the low word at its midpoint — 5 LOP3 + 2 VIMNMX3
-// instead of 4 DSETP + 8 FSEL (16 issue slots -> 7).  Only eps = 1e-6 max(v^2) + floor uses it (derivatives.jl:71): a relative
-// error of 2^-21 in the maximum changes eps by <= 1e-6 relative, which moves the C3 128^3 result after 100 RK3 steps from 5.5e-15
-// to 8.5e-14 of the oracle (bar 1e-10; tests/test_gpu_parity.py::test_config_parity_survey_sizes prints the observed value).
+// max|a..e| to 20 significant bits in 2-3 instructions instead of 4 DSETP + 8 FSEL (16 issue slots): the HIGH words of the five
+// doubles are compared as Float32 bit patterns with the |.| operand modifier (FMNMX / FMNMX3: sign-cleared IEEE patterns of either
+// width order like their magnitudes; a double high word is a finite Float32 pattern for |x| < 2^1017), and the result keeps the
+// low word of `a`, which is dead afterwards — so no register move is needed to build the pair.  Only eps = 1e-6 max(v^2) + floor
+// uses it (derivatives.jl:71): a relative error < 2^-20 in the maximum changes eps by < 2e-6 relative, which moves the C3 128^3
+// result after 100 RK3 steps from 5.5e-15 to ~1e-13 of the oracle (bar 1e-10; tests/test_gpu_parity.py::
+// test_config_parity_survey_sizes prints the observed value).  NaN / Inf inputs drop out of the maximum but still poison the
+// smoothness indicators, like in the reference.  Used by the x-pair kernel (pure advection) only: with the curvature term on
+// kinked data (C2 at 512^2) rounding-level differences are amplified ~1e4-fold over 100 steps (the strict kernel itself is
+// 4.6e-12 from the oracle there), so the general tiled kernels keep the exact maximum.
 __device__ __forceinline__ double absmax5_hi(double a, double b, double c, double d, double e) {
-    const unsigned ha = (unsigned)__double2hiint(a) & 0x7fffffffu, hb = (unsigned)__double2hiint(b) & 0x7fffffffu,
-                   hc = (unsigned)__double2hiint(c) & 0x7fffffffu, hd = (unsigned)__double2hiint(d) & 0x7fffffffu,
-                   he = (unsigned)__double2hiint(e) & 0x7fffffffu;
-    const unsigned m = max(max(max(ha, hb), max(hc, hd)), he);
-    return __hiloint2double((int)m, (int)0x80000000u);
+    const float fa = __int_as_float(__double2hiint(a)), fb = __int_as_float(__double2hiint(b)), fc = __int_as_float(__double2hiint(c)),
+                fd = __int_as_float(__double2hiint(d)), fe = __int_as_float(__double2hiint(e));
+    const float m = fmaxf(fmaxf(fmaxf(fabsf(fa), fabsf(fb)), fabsf(fc)), fmaxf(fabsf(fd), fabsf(fe)));
+    return __hiloint2double(__float_as_int(m), __double2loint(a));
 }
 
 // Undivided upwind WENO5: given six samples in upwind order (q3 is the node, q0 the far upwind
@@ -111,12 +116,15 @@ __device__ __forceinline__ double absmax5_hi(double a, double b, double c, doubl
 // parameters (constant bank): as literals the compiler re-materialises them with 10 UMOV per node, from the constant bank
 // it takes 3 uniform loads.
 
+// weno5_up_f64: first differences in the storage type, everything after in Float64 — Julia's promotion for Float32 fields
+// (all literals of derivatives.jl:61-81 are Float64).  weno5_up<T> below is this for T = double and the all-FP32 evaluation for
+// T = float.
 template <class T>
-__device__ __forceinline__ double weno5_up(const WenoK& K, T q0, T q1, T q2, T q3, T q4, T q5) {
+__device__ __forceinline__ double weno5_up_f64(const WenoK& K, T q0, T q1, T q2, T q3, T q4, T q5) {
     const double d0 = double(T(q1 - q0)), d1 = double(T(q2 - q1)), d2 = double(T(q3 - q2)),
                  d3 = double(T(q4 - q3)), d4 = double(T(q5 - q4));
     const double e1 = d1 - d0, e2 = d2 - d1, e3 = d3 - d2, e4 = d4 - d3;
-    const double m = absmax5_hi(d0, d1, d2, d3, d4);
+    const double m = absmax5(d0, d1, d2, d3, d4);
     const double eps = fma(K.e6, m * m, K.fl);
     const double c133 = K.c133;
     const double t1a = e2 - e1, t1b = e3 - e2, t1c = e4 - e3;
@@ -133,6 +141,9 @@ __device__ __forceinline__ double weno5_up(const WenoK& K, T q0, T q1, T q2, T q
     const double num = fma(w3, G3, fma(w2, G2, w1 * G1));
     return fma(num, fast_rcp<1>(den), d2);
 }
+
+template <class T>
+__device__ __forceinline__ double weno5_up(const WenoK& K, T q0, T q1, T q2, T q3, T q4, T q5) { return weno5_up_f64<T>(K, q0, q1, q2, q3, q4, q5); }
 
 // Float32 fields: the same evaluation entirely in FP32 (FFMA issues at <= 1 slot, FP64 at 2; BASELINE tolerance for
 // Float32 is 1e-4 against the oracle, which follows Julia's promotion to Float64 after the first difference).

@@ -342,7 +342,10 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
                             // s from the sign bits (integer ops instead of 8 DSETP): when u*g == 0 the reference takes the plus-biased
                             // stencil but multiplies it by zero, so either ordering yields the same 0 contribution (a == 0).
                             const int s = ((__double2hiint(u) ^ ghi) >> 31) | 1;                 // = sign(u*g); upwind-ordered sampling: q_k = phi[i - s*(3-k)]
-                            const double w = weno5_up<T>(A.wk, up(d, -3, s), up(d, -2, s), up(d, -1, s), qc, up(d, 1, s), up(d, 2, s));
+                            // 2-D Float32 kernels are not faster with the FP32 evaluation (they are latency / fill bound) and C2's curvature term
+                            // amplifies its 1e-7 deviations past the 1e-4 bar at 512^2 (notch corners): they take Julia's promoted form
+                            const double w = (NDIM == 2 || !ONE) ? weno5_up_f64<T>(A.wk, up(d, -3, s), up(d, -2, s), up(d, -1, s), qc, up(d, 1, s), up(d, 2, s))
+                                                                 : weno5_up<T>(A.wk, up(d, -3, s), up(d, -2, s), up(d, -1, s), qc, up(d, 1, s), up(d, 2, s));
                             const double a = fabs(u) * (fabs(g) * ih[d]);
                             if (do_cfl) sest = d == 0 ? a : sest + a;       // = sum_d |u_d| |g_stage| / h_d, compared with tau |g_stage / g_next|
                             H = d == 0 ? a * w : fma(a, w, H);
@@ -602,7 +605,7 @@ bool stage_tiled_supported(int ndim, const StageParams<T>& P) {
 }
 
 template <class T>
-cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, cudaStream_t s, bool allow_pair, int* used_pair) {
+cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, cudaStream_t s, int pair_mode, int* used_pair) {
     if (!stage_tiled_supported<T>(ndim, P)) return cudaErrorNotSupported;
     if (P.r1 <= P.r0) return cudaSuccess;
     AuxList A{};
@@ -619,8 +622,8 @@ cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, 
         }
     }
     if (P.p0) { A.p0 = A.n; A.src[A.n++] = P.p0; }
-    if (allow_pair && ndim == 3 && mask == M_ADV_WENO) {      // headline path: x-pair kernel (lsm_pair3d.cu); falls through when it does not apply
-        const cudaError_t e = launch_stage_pair3d<T>(P, A, s);
+    if (pair_mode && ndim == 3 && mask == M_ADV_WENO) {      // headline path: x-pair kernel (lsm_pair3d.cu); falls through when it does not apply
+        const cudaError_t e = launch_stage_pair3d<T>(P, A, s, pair_mode == 2);
         if (e != cudaErrorNotSupported) { if (used_pair) *used_pair = 1; return e; }
     }
     bool remap = true;     // every BC an index map?  (ExtrapolationBC{P>=1} is a weighted stencil)
@@ -635,11 +638,11 @@ cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, 
 // instantiations build in parallel; without either macro both are instantiated here.
 #if !defined(LSM_TILED_F64)
 template bool stage_tiled_supported<float>(int, const StageParams<float>&);
-template cudaError_t launch_stage_tiled<float>(int, const StageParams<float>&, int, cudaStream_t, bool, int*);
+template cudaError_t launch_stage_tiled<float>(int, const StageParams<float>&, int, cudaStream_t, int, int*);
 #endif
 #if !defined(LSM_TILED_F32)
 template bool stage_tiled_supported<double>(int, const StageParams<double>&);
-template cudaError_t launch_stage_tiled<double>(int, const StageParams<double>&, int, cudaStream_t, bool, int*);
+template cudaError_t launch_stage_tiled<double>(int, const StageParams<double>&, int, cudaStream_t, int, int*);
 #endif
 
 }  // namespace lsm

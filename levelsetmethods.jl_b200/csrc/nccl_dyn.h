@@ -27,7 +27,8 @@ struct NcclApi {
             if (handle) break;
         }
         if (!handle) { *why = dlerror(); return false; }
-#define LSM_SYM(field, sym) field = reinterpret_cast<decltype(field)>(dlsym(handle, sym)); if (!field) { *why = "missing NCCL symbol " sym; return false; }
+#define LSM_SYM(field, sym) field = reinterpret_cast<decltype(field)>(dlsym(handle, sym)); \
+        if (!field) { *why = "missing NCCL symbol " sym; dlclose(handle); handle = nullptr; return false; }
         LSM_SYM(GetUniqueId, "ncclGetUniqueId")
         LSM_SYM(CommInitRank, "ncclCommInitRank")
         LSM_SYM(CommDestroy, "ncclCommDestroy")

@@ -269,9 +269,11 @@ PAIR_BCS = [("neumann",), ("periodic",), ("symmetry",),
 @pytest.mark.parametrize("n", PAIR_SHAPES, ids=["x".join(map(str, s)) for s in PAIR_SHAPES])
 def test_pair_kernel_bitwise_vs_tiled(m, n):
     """The x-pair kernel (csrc/lsm_pair3d.cu: TMA for every tile, lazy ghost fix-up, direction branches, shared differences)
-    performs the same operations as the general tiled kernel, so LSM_OPT_KERNEL = 0 and 3 must give BIT-IDENTICAL states:
+    performs the same operations as the general tiled kernel when it is run with the exact epsilon maximum (LSM_OPT_KERNEL = 4;
+    anisotropic mesh sizes, so the per-dimension scaling is not folded), so kernels 4 and 3 must give BIT-IDENTICAL states:
     partial tiles on every side, every index-map BC (also mixed per side), FE / RK2 / RK3, stored and separable velocity,
-    sign changes of the velocity inside warps and pairs, both dtypes."""
+    sign changes of the velocity inside warps and pairs, both dtypes.  The default mode (20-bit epsilon maximum) must stay at
+    rounding level of it."""
     ctx = m.default_context()
     k = 0
     for bc in PAIR_BCS:
@@ -282,7 +284,7 @@ def test_pair_kernel_bitwise_vs_tiled(m, n):
             case = _pair_case(n, bc, dtype, separable=(k % 3 == 0))
             integ = (m.RK3, m.RK2, m.ForwardEuler)[k % 3]
             outs = []
-            for kernel in (0, 3):
+            for kernel in (4, 3, 0):
                 ctx.set_option(OPT_KERNEL, kernel)
                 ctx.reset_counters()
                 phi = case.engine_field(m)
@@ -291,9 +293,84 @@ def test_pair_kernel_bitwise_vs_tiled(m, n):
                 m.integrate(eq, 3 * dt * (1 - 1e-12))
                 outs.append((eq.t, eq.steps_taken, eq.state.peek().copy(), ctx.counters()["pair_launches"]))
             ctx.set_option(OPT_KERNEL, 0)
-            assert outs[0][3] > 0 and outs[1][3] == 0, "kernel selection"
-            assert outs[0][:2] == outs[1][:2]
+            assert outs[0][3] > 0 and outs[1][3] == 0 and outs[2][3] > 0, "kernel selection"
+            assert outs[0][:2] == outs[1][:2] == outs[2][:2]
             assert np.array_equal(outs[0][2], outs[1][2]), (n, bc, np.dtype(dtype).name, float(np.abs(outs[0][2] - outs[1][2]).max()))
+            tol = 1e-12 if dtype == np.float64 else 0.0
+            assert np.abs(outs[2][2].astype(np.float64) - outs[1][2].astype(np.float64)).max() <= tol
+
+
+def _notched_sphere_case(n, dtype=np.float64):
+    """3-D Zalesak-type body (sphere with a slot: kinks along the slot edges) in the Enright velocity: the sharp-feature
+    counterpart of C3 for the x-pair kernel."""
+    case = H.c3_enright(n, dtype)
+    x, y, z = H.coords(case.lc, case.hc, case.n)
+    sphere = np.sqrt((x - 0.5) ** 2 + (y - 0.6) ** 2 + (z - 0.5) ** 2) - 0.25
+    slot = np.maximum(np.abs(x - 0.5) - 0.05, np.abs(y - 0.5) - 0.25) + 0 * z
+    case.phi0 = np.asfortranarray(np.maximum(sphere, -slot).astype(dtype))
+    return case
+
+
+def test_pair_kernel_kinked_body_parity(m, O):
+    """Default kernels on non-smooth data, 96^3 cube (isotropic mesh: folded scaling + 20-bit epsilon maximum), 100 RK3 steps
+    against the oracle: the BASELINE bar with the observed value printed."""
+    O.set_threads(O.max_threads())
+    a, b, t, n = run_pair(m, O, _notched_sphere_case(96), integ="RK3", steps=100)
+    d = check_parity(a, b, 1e-10)
+    print(f"PARITY notched-sphere-96 float64: {n} steps, max-abs diff {d:.3e} (bar 1e-10)")
+    assert d <= 2e-11
+
+
+def test_cfl_candidates_are_exact(m, O):
+    """Time-scaled static coefficients: from the third CFL request on, the maximum is evaluated on the HOST over the candidate
+    nodes (lsm_api.cu, CflCand) — no reduction pass, no D2H, no sync per step.  It must be bit-identical to the full reduction
+    (LSM_OPT_CFL_CANDIDATES = 0) for every scale: stored and separable velocity, both dtypes, a scalar speed, a field of ties
+    (constant velocity stored as a field: the candidate list overflows and the regular path answers), and whole integrations
+    must take the same steps and produce the same bits."""
+    OPT_FUSE, OPT_CAND = 4, 6
+    ctx = m.default_context()
+    cases = [H.c3_enright(40), H.c3_enright(40, separable=True), H.c3_enright(32, np.float32), H.c1_circle_rotation(96)]
+    cases[3].terms[0]["cos_period"] = 2.0
+    flat = H.c3_enright(24)
+    flat.terms[0]["field"] = np.broadcast_to(np.array([0.3, -0.2, 0.1]).reshape(3, 1, 1, 1), (3, 24, 24, 24)).copy()
+    cases.append(flat)
+    ts = [0.0, 0.11, 0.37, 0.9, 1.4, 1.5 - 1e-9, 2.2, 2.9]
+    for case in cases:
+        fo, to = case.oracle_field(), case.oracle_terms()
+        phi = case.engine_field(m)
+        terms = case.engine_terms(m, phi)
+        ctx.reset_counters()
+        got = [m.compute_cfl(terms, phi, t) for t in ts]
+        passes = ctx.counters()["cfl_passes"]
+        assert got == [O.compute_cfl(fo, to, t) for t in ts], case.name
+        if case is not flat:
+            assert passes <= 2, (case.name, passes)                    # first request + the unscaled maximum of the build
+    # normal motion with a time-scaled stored speed (host g(t)): |fl(v g)| is monotone in |v|
+    g = m.CartesianGrid((-1, -1), (1, 1), (80, 64))
+    X, Y = g.coords()
+    v = np.asfortranarray(0.3 + 0.2 * np.sin(3 * X) * np.cos(2 * Y))
+    phi = m.MeshField(np.asfortranarray(np.hypot(X, Y) - 0.5), g, bc=m.NeumannBC())
+    term = m.NormalMotionTerm(m.TimeScaled(m.MeshField(v, g), lambda t: math.cos(t) - 0.2))
+    ref = []
+    for opt in (0, 1):
+        ctx.set_option(OPT_CAND, opt)
+        ref.append([m.compute_cfl((term,), phi, t) for t in ts])
+    assert ref[0] == ref[1]
+    # whole integrations: identical step counts, times and states with and without candidates (and without the fused CFL)
+    for case in (H.c3_enright(40), H.c3_enright(40, separable=True)):
+        outs = []
+        for cand, fuse in ((1, 1), (0, 1), (0, 0)):
+            ctx.set_option(OPT_CAND, cand); ctx.set_option(OPT_FUSE, fuse)
+            phi = case.engine_field(m)
+            eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=m.RK3())
+            ctx.reset_counters()
+            m.integrate(eq, 0.25)
+            outs.append((eq.t, eq.steps_taken, eq.state.peek().copy(), ctx.counters()))
+        ctx.set_option(OPT_CAND, 1); ctx.set_option(OPT_FUSE, 1)
+        assert outs[0][1] > 12
+        for o in outs[1:]:
+            assert o[:2] == outs[0][:2] and np.array_equal(o[2], outs[0][2])
+        assert outs[0][3]["d2h_bytes"] < outs[1][3]["d2h_bytes"]       # no 8-byte readback per step any more
 
 
 def test_against_committed_vectors(m):
