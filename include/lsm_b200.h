@@ -220,6 +220,21 @@ int32_t lsm_extend_along_normals(lsm_ctx* ctx, lsm_field* F, lsm_field* phi, int
 enum { LSM_CSG_UNION = 0, LSM_CSG_INTERSECT = 1, LSM_CSG_SETDIFF = 2, LSM_CSG_COMPLEMENT = 3 };
 int32_t lsm_field_csg(lsm_ctx* ctx, lsm_field* dst, const lsm_field* src, int32_t op);
 
+/* Analytic initial conditions and coefficients generated ON THE DEVICE ("next" row 3): the reference builds them with
+ * MeshField(f, grid) (meshfield.jl:208-211: f evaluated at x = lc + (I-1) h, meshes.jl:115-117) and combines them with the set
+ * operations above (docs/src/example-zalesak.md:21-40).  A 1024^3 configuration is 60 GB of fields: generating them in HBM avoids
+ * building and uploading them from the host.  Operation order (no FMA), so that a NumPy restatement is bit-identical:
+ *   LSM_SHAPE_SPHERE  params = c[ndim], r        sqrt(((x1-c1)^2 + (x2-c2)^2) + (x3-c3)^2) - r
+ *   LSM_SHAPE_BOX     params = c[ndim], w[ndim]  max_d (|x_d - c_d| - w_d / 2)           (the notch of the Zalesak disk)
+ *   LSM_SHAPE_PLANE   params = n[ndim], offset   ((n1 x1 + n2 x2) + n3 x3) - offset
+ *   LSM_SHAPE_CONST   params = v[ncomp]          every node of component c = v[c]        (scalar or vector fields)
+ * with x_d = lc_d + i_d * h_d, i_d the 0-based GLOBAL node index.  Values are rounded to the field's dtype at the end. */
+enum { LSM_SHAPE_SPHERE = 0, LSM_SHAPE_BOX = 1, LSM_SHAPE_PLANE = 2, LSM_SHAPE_CONST = 3 };
+int32_t lsm_field_fill_shape(lsm_field* f, int32_t shape, const double* params, int32_t nparams);
+/* Materialise a separable velocity (lsm_field_create_separable) into a stored vector field:
+ * u_d[i,j,k] = ((scale_d * X_d[i]) * Y_d[j]) * Z_d[k] — rigid rotation, shear, the Enright field ... from 3 x ndim small tables. */
+int32_t lsm_field_fill_separable(lsm_field* dst, const lsm_field* sep);
+
 /* ---- diagnostics (test harness) -------------------------------------------- */
 /* max |a - b| over all owned nodes, all-reduced over ranks. */
 int32_t lsm_max_abs_diff(lsm_ctx* ctx, const lsm_field* a, const lsm_field* b, double* out);

@@ -21,6 +21,7 @@ TERM_ADVECTION, TERM_NORMAL, TERM_CURVATURE, TERM_EIKONAL = 0, 1, 2, 3
 UPWIND, WENO5 = 0, 1
 COEF_CONST, COEF_FIELD, COEF_SEPARABLE, COEF_NONE = 0, 1, 2, 3
 TS_NONE, TS_COS, TS_HOST = 0, 1, 2
+SHAPE_SPHERE, SHAPE_BOX, SHAPE_PLANE, SHAPE_CONST = 0, 1, 2, 3
 FORWARD_EULER, RK2, RK3 = 0, 1, 2
 OPT_KERNEL, OPT_TIME_STAGES, OPT_CFL_CACHE, OPT_OVERLAP, OPT_FUSE_CFL, OPT_GRAPH, OPT_CFL_CANDIDATES = 0, 1, 2, 3, 4, 5, 6
 MAX_TERMS = 4
@@ -83,6 +84,8 @@ SYMBOLS = {
     "lsm_field_create": (_i32, [_vp, _i32, _pi32, _i32, _i32, _pdbl, _pdbl, C.POINTER(_vp)]),
     "lsm_field_create_separable": (_i32, [_vp, _i32, _pi32, _pdbl, _pdbl, _pdbl, _pdbl, C.POINTER(_vp)]),
     "lsm_field_destroy": (_i32, [_vp]),
+    "lsm_field_fill_shape": (_i32, [_vp, _i32, _pdbl, _i32]),
+    "lsm_field_fill_separable": (_i32, [_vp, _vp]),
     "lsm_field_set_bc": (_i32, [_vp, C.POINTER(lsm_bc)]),
     "lsm_field_local_extent": (_i32, [_vp, _pi32, _pi32]),
     "lsm_field_upload": (_i32, [_vp, _vp]),

@@ -291,18 +291,63 @@ class MeshField:
         else:
             raise ValueError(f"values of shape {vals.shape} do not match the grid {grid.n}")
         self._vals = np.array(vals, dtype=dtype, order="F", copy=True)
+        self._shape, self._dtype = self._vals.shape, self._vals.dtype
         self.bcs = None if bc is None else _normalize_bc(bc, N)
         self._dev = None          # lsm_field handle
         self._dev_bcs = None
         self._host_fresh, self._dev_fresh = True, False
         self._borrowed = False
 
+    # --- fields generated on the device (no host array until someone asks for the values) ---
+    @classmethod
+    def _device_only(cls, grid: CartesianGrid, ncomp: int, bc, dtype, ctx: Optional[Context]) -> "MeshField":
+        f = cls.__new__(cls)
+        f.mesh, f.ctx = grid, (ctx if ctx is not None else default_context())
+        nr = f.ctx.nranks
+        f._first, f._count = (f.ctx.slab(grid.n[-1]) if nr > 1 else (0, grid.n[-1]))
+        local = tuple(grid.n[:-1]) + (f._count,)
+        f.ncomp = ncomp
+        f._shape = local if ncomp == 1 else (ncomp,) + local
+        f._dtype = np.dtype(dtype or np.float64)
+        f._vals = None
+        f.bcs = None if bc is None else _normalize_bc(bc, grid.ndim)
+        f._dev, f._dev_bcs, f._borrowed = None, None, False
+        f._host_fresh, f._dev_fresh = False, True
+        f._create_device()
+        return f
+
+    @classmethod
+    def from_shape(cls, grid: CartesianGrid, shape: str, params, bc=None, dtype=None, ctx: Optional[Context] = None) -> "MeshField":
+        """Engine extension: ``MeshField(f, grid)`` for an analytic ``f`` evaluated on the DEVICE (``lsm_field_fill_shape``):
+        ``"sphere"`` (centre..., radius), ``"box"`` (centre..., widths...), ``"plane"`` (normal..., offset), ``"const"`` (value)."""
+        code = {"sphere": L.SHAPE_SPHERE, "box": L.SHAPE_BOX, "plane": L.SHAPE_PLANE, "const": L.SHAPE_CONST}[shape]
+        p = [float(v) for v in np.ravel(np.asarray(params, dtype=np.float64))]
+        f = cls._device_only(grid, len(p) if (shape == "const" and len(p) > 1) else 1, bc, dtype, ctx)
+        L.check(L.lib().lsm_field_fill_shape(f._dev, code, (C.c_double * len(p))(*p), len(p)))
+        return f
+
+    @classmethod
+    def from_separable(cls, sep: "SeparableVelocity", dtype=None, ctx: Optional[Context] = None) -> "MeshField":
+        """Engine extension: the stored velocity field ``u_d = ((s_d X_d[i]) Y_d[j]) Z_d[k]`` of a :class:`SeparableVelocity`,
+        materialised on the device (``lsm_field_fill_separable``) — bit-identical to building it with NumPy and uploading."""
+        ctx = ctx if ctx is not None else (sep.ctx or default_context())
+        if sep.ctx is None:
+            sep.ctx = ctx
+        f = cls._device_only(sep.grid, sep.grid.ndim, None, dtype, ctx)
+        L.check(L.lib().lsm_field_fill_separable(f._dev, sep.device()))
+        return f
+
+    def _host(self) -> np.ndarray:
+        if self._vals is None:
+            self._vals = np.empty(self._shape, dtype=self._dtype, order="F")
+        return self._vals
+
     # --- getters (meshfield.jl:58-64) ---
     @property
     def vals(self) -> np.ndarray:
         """``values(phi)``.  Syncs from the device if it is ahead; the caller may mutate the array."""
         if not self._host_fresh:
-            L.check(L.lib().lsm_field_download(self._dev, self._vals.ctypes.data))
+            L.check(L.lib().lsm_field_download(self._dev, self._host().ctypes.data))
             self._host_fresh = True
         self._dev_fresh = False      # conservative: the caller may write through the returned array
         return self._vals
@@ -312,7 +357,7 @@ class MeshField:
     def peek(self) -> np.ndarray:
         """Read-only look at the current values (does not invalidate the device copy)."""
         if not self._host_fresh:
-            L.check(L.lib().lsm_field_download(self._dev, self._vals.ctypes.data))
+            L.check(L.lib().lsm_field_download(self._dev, self._host().ctypes.data))
             self._host_fresh = True
         v = self._vals.view()
         v.flags.writeable = False
@@ -324,7 +369,7 @@ class MeshField:
 
     @property
     def valtype(self):
-        return self._vals.dtype
+        return self._dtype
 
     def has_boundary_conditions(self):
         return self.bcs is not None
@@ -348,18 +393,22 @@ class MeshField:
             self.ctx = default_context()
         return self.ctx
 
+    def _create_device(self):
+        lib, ctx = L.lib(), self._context()
+        h = C.c_void_p()
+        g = self.mesh
+        n = (C.c_int32 * 3)(*g.n, *([1] * (3 - g.ndim)))
+        lc = (C.c_double * 3)(*g.lc, *([0.0] * (3 - g.ndim)))
+        hc = (C.c_double * 3)(*g.hc, *([1.0] * (3 - g.ndim)))
+        dt = L.F32 if self._dtype == np.float32 else L.F64
+        L.check(lib.lsm_field_create(ctx.handle, g.ndim, n, dt, self.ncomp, lc, hc, C.byref(h)))
+        self._dev = h
+
     def device(self):
         """The up-to-date ``lsm_field`` handle (creating / uploading as needed)."""
-        lib, ctx = L.lib(), self._context()
+        lib = L.lib()
         if self._dev is None:
-            h = C.c_void_p()
-            g = self.mesh
-            n = (C.c_int32 * 3)(*g.n, *([1] * (3 - g.ndim)))
-            lc = (C.c_double * 3)(*g.lc, *([0.0] * (3 - g.ndim)))
-            hc = (C.c_double * 3)(*g.hc, *([1.0] * (3 - g.ndim)))
-            dt = L.F32 if self._vals.dtype == np.float32 else L.F64
-            L.check(lib.lsm_field_create(ctx.handle, g.ndim, n, dt, self.ncomp, lc, hc, C.byref(h)))
-            self._dev = h
+            self._create_device()
         if self.bcs is not None and self._dev_bcs != self.bcs:
             arr = (L.lsm_bc * 6)()
             for d, (l, r) in enumerate(self.bcs):
@@ -381,7 +430,7 @@ class MeshField:
         f = cls.__new__(cls)
         f.mesh, f.ctx, f.ncomp, f.bcs = like.mesh, like.ctx, 1, like.bcs
         f._first, f._count = like._first, like._count
-        f._vals = np.empty_like(like._vals)
+        f._vals, f._shape, f._dtype = None, like._shape, like._dtype      # host array allocated on first read
         f._dev, f._dev_bcs = handle, like.bcs
         f._host_fresh, f._dev_fresh, f._borrowed = False, True, True
         return f
@@ -397,7 +446,7 @@ class MeshField:
         idx = (C.c_int32 * len(I))(*[int(i) for i in I])
         out = C.c_double()
         L.check(L.lib().lsm_field_getindex(self.device(), idx, 1, C.byref(out)))
-        return float(out.value) if self._vals.dtype == np.float64 else float(np.float32(out.value))
+        return float(out.value) if self._dtype == np.float64 else float(np.float32(out.value))
 
     def __setitem__(self, I, val):
         if not isinstance(I, tuple):
@@ -406,6 +455,11 @@ class MeshField:
 
     # --- copy / copy! / map (meshfield.jl:161-169,275-278) ---
     def copy(self) -> "MeshField":
+        if self._vals is None or not self._host_fresh:
+            # the device holds the current values (device-generated or advanced by the engine): copy there, no host round trip
+            f = MeshField._device_only(self.mesh, self.ncomp, self.bcs, self._dtype, self.ctx)
+            L.check(L.lib().lsm_field_copy(f._dev, self.device()))
+            return f
         return MeshField(self.peek().copy(order="F"), self.mesh, bc=None if self.bcs is None else self.bcs, ctx=self.ctx)
 
     def copy_from(self, src: "MeshField") -> "MeshField":
@@ -424,7 +478,7 @@ class MeshField:
             pass
 
     def __repr__(self):
-        return f"MeshField on {self.mesh!r}, valtype={self._vals.dtype}, bc={self.bcs}"
+        return f"MeshField on {self.mesh!r}, valtype={self._dtype}, bc={self.bcs}"
 
 
 def _add_boundary_conditions(phi: MeshField, bc) -> MeshField:

@@ -1265,6 +1265,40 @@ int32_t lsm_field_csg(lsm_ctx* ctx, lsm_field* dst, const lsm_field* src, int32_
     return LSM_OK;
 }
 
+int32_t lsm_field_fill_shape(lsm_field* f, int32_t shape, const double* params, int32_t nparams) {
+    if (!f || !params) return fail(LSM_ERR_ARG, "null argument");
+    if (f->separable) return fail(LSM_ERR_ARG, "cannot fill a separable field");
+    if (shape < LSM_SHAPE_SPHERE || shape > LSM_SHAPE_CONST) return fail(LSM_ERR_ARG, "unknown shape %d", shape);
+    const int want = shape == LSM_SHAPE_SPHERE || shape == LSM_SHAPE_PLANE ? f->ndim + 1 : shape == LSM_SHAPE_BOX ? 2 * f->ndim : f->ncomp;
+    if (nparams != want) return fail(LSM_ERR_ARG, "shape %d on a %d-D field takes %d parameters (got %d)", shape, f->ndim, want, nparams);
+    if (shape != LSM_SHAPE_CONST && f->ncomp != 1) return fail(LSM_ERR_ARG, "shapes fill scalar fields");
+    lsm_ctx* ctx = f->ctx;
+    CU(cudaSetDevice(ctx->device));
+    ShapeParams P{};
+    P.shape = shape; P.ndim = f->ndim; P.ncomp = f->ncomp; P.first_last = f->first_last; P.cstride = f->cstride;
+    for (int d = 0; d < 3; ++d) { P.n[d] = f->n[d]; P.lc[d] = f->lc[d]; P.h[d] = d < f->ndim ? f->h[d] : 0.0; }
+    for (int k = 0; k < nparams; ++k) P.p[k] = params[k];
+    cudaError_t e = launch_fill_shape(f->dtype == LSM_F64, f->p, P, ctx->stream);
+    if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->cnt.kernel_launches += 1;
+    f->version++; f->halo_valid = false;
+    return LSM_OK;
+}
+
+int32_t lsm_field_fill_separable(lsm_field* dst, const lsm_field* sep) {
+    if (!dst || !sep) return fail(LSM_ERR_ARG, "null argument");
+    if (!sep->separable || dst->separable) return fail(LSM_ERR_ARG, "lsm_field_fill_separable(dst, sep): sep must come from lsm_field_create_separable, dst must be a stored field");
+    if (dst->ctx != sep->ctx || dst->ndim != sep->ndim || dst->ncomp != sep->ndim) return fail(LSM_ERR_ARG, "destination must be a vector field of the same context and dimension");
+    for (int d = 0; d < dst->ndim; ++d) if (dst->nglob[d] != sep->nglob[d]) return fail(LSM_ERR_ARG, "shape mismatch along dim %d", d + 1);
+    lsm_ctx* ctx = dst->ctx;
+    CU(cudaSetDevice(ctx->device));
+    cudaError_t e = launch_fill_separable(dst->dtype == LSM_F64, dst->p, dst->cstride, dst->n, dst->ndim, sep->scale, sep->tab, ctx->stream);
+    if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->cnt.kernel_launches += 1;
+    dst->version++; dst->halo_valid = false;
+    return LSM_OK;
+}
+
 int32_t lsm_max_abs_diff(lsm_ctx* ctx, const lsm_field* a, const lsm_field* b, double* out) {
     if (!ctx || !a || !b || !out) return fail(LSM_ERR_ARG, "null argument");
     if (a->ctx != ctx || b->ctx != ctx || a->dtype != b->dtype || a->ncomp != 1 || b->ncomp != 1 || a->owned != b->owned)

@@ -10,6 +10,7 @@
 //   meshfield.jl:213-260 getindex/_getindexbc, boundaryconditions.jl:90-153 bc_stencil,
 //   derivatives.jl:28-175, levelsetops.jl:197-244 curvature, levelsetterms.jl:73-265 terms,
 //   timestepping.jl:128-202 stage combinations.
+#include <algorithm>
 #include "lsm_dev.cuh"
 #include "lsm_bc.cuh"
 #include "lsm_kernels.h"
@@ -482,6 +483,87 @@ cudaError_t launch_cfl_candidates(int ndim, int dtype_f64, const CandParams& P, 
                           else cfl_candidates_kernel<NN, float><<<(unsigned)grid, block, 0, s>>>(P); } while (0)
     if (ndim == 1) LSM_CAND(1); else if (ndim == 2) LSM_CAND(2); else LSM_CAND(3);
 #undef LSM_CAND
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// analytic initial conditions / coefficients generated on the device.  MeshField(f, grid) (meshfield.jl:208-211) evaluates
+// f at x = lc + (I - 1) h (meshes.jl:115-117); these kernels do the same for a small family of f, in the operation order
+// stated in include/lsm_b200.h (this file is compiled without FMA contraction, so a NumPy restatement is bit-identical).
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__global__ void fill_shape_kernel(T* __restrict__ dst, const __grid_constant__ ShapeParams P) {
+    const long total = (long)P.n[0] * P.n[1] * P.n[2];
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        int I[3];
+        I[0] = (int)(idx % P.n[0]);
+        const long q = idx / P.n[0];
+        I[1] = (int)(q % P.n[1]);
+        I[2] = (int)(q / P.n[1]);
+        I[P.ndim - 1] += P.first_last;
+        double x[3];
+        for (int d = 0; d < 3; ++d) x[d] = P.lc[d] + double(I[d]) * P.h[d];
+        if (P.shape == 3) {                                   // CONST: one value per component
+            for (int c = 0; c < P.ncomp; ++c) dst[(long)c * P.cstride + idx] = T(P.p[c]);
+            continue;
+        }
+        double v = 0.0;
+        if (P.shape == 0) {                                   // SPHERE: sqrt(sum_d (x_d - c_d)^2) - r
+            double s = 0.0;
+            for (int d = 0; d < P.ndim; ++d) { const double t = x[d] - P.p[d]; s = d == 0 ? t * t : s + t * t; }
+            v = sqrt(s) - P.p[P.ndim];
+        } else if (P.shape == 1) {                            // BOX: max_d (|x_d - c_d| - w_d / 2)
+            for (int d = 0; d < P.ndim; ++d) {
+                const double t = fabs(x[d] - P.p[d]) - P.p[P.ndim + d] / 2.0;
+                v = d == 0 ? t : (t > v ? t : v);
+            }
+        } else {                                              // PLANE: sum_d n_d x_d - offset
+            double s = 0.0;
+            for (int d = 0; d < P.ndim; ++d) { const double t = P.p[d] * x[d]; s = d == 0 ? t : s + t; }
+            v = s - P.p[P.ndim];
+        }
+        dst[idx] = T(v);
+    }
+}
+
+cudaError_t launch_fill_shape(int f64, void* dst, const ShapeParams& P, cudaStream_t s) {
+    const long total = (long)P.n[0] * P.n[1] * P.n[2];
+    const int block = 256;
+    const long grid = std::min<long>((total + block - 1) / block, 148L * 16);
+    if (f64) fill_shape_kernel<double><<<(unsigned)std::max<long>(grid, 1), block, 0, s>>>(static_cast<double*>(dst), P);
+    else fill_shape_kernel<float><<<(unsigned)std::max<long>(grid, 1), block, 0, s>>>(static_cast<float*>(dst), P);
+    return cudaGetLastError();
+}
+
+struct SepParams { int n[3]; int ndim; long cstride; double scale[3]; const double* tab[3][3]; };
+
+// component d of a separable vector field, materialised in SoA storage: ((scale_d * X_d[i]) * Y_d[j]) * Z_d[k]
+template <class T>
+__global__ void fill_separable_kernel(T* __restrict__ dst, const __grid_constant__ SepParams P) {
+    const long total = (long)P.n[0] * P.n[1] * P.n[2];
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i0 = (int)(idx % P.n[0]);
+        const long q = idx / P.n[0];
+        const int i1 = (int)(q % P.n[1]);
+        const int i2 = (int)(q / P.n[1]);
+        for (int d = 0; d < P.ndim; ++d) {
+            double v = P.scale[d] * P.tab[d][0][i0];
+            if (P.ndim > 1) v = v * P.tab[d][1][i1];
+            if (P.ndim > 2) v = v * P.tab[d][2][i2];
+            dst[(long)d * P.cstride + idx] = T(v);
+        }
+    }
+}
+
+cudaError_t launch_fill_separable(int f64, void* dst, long cstride, const int* n, int ndim, const double* scale, const double* const (*tab)[3], cudaStream_t s) {
+    SepParams P{};
+    for (int d = 0; d < 3; ++d) { P.n[d] = n[d]; P.scale[d] = scale[d]; for (int a = 0; a < 3; ++a) P.tab[d][a] = tab[d][a]; }
+    P.ndim = ndim; P.cstride = cstride;
+    const long total = (long)n[0] * n[1] * n[2];
+    const int block = 256;
+    const long grid = std::max<long>(1, std::min<long>((total + block - 1) / block, 148L * 16));
+    if (f64) fill_separable_kernel<double><<<(unsigned)grid, block, 0, s>>>(static_cast<double*>(dst), P);
+    else fill_separable_kernel<float><<<(unsigned)grid, block, 0, s>>>(static_cast<float*>(dst), P);
     return cudaGetLastError();
 }
 

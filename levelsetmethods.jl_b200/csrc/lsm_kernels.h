@@ -32,6 +32,17 @@ cudaError_t launch_transpose(int f64, bool to_soa, const void* src, void* dst, l
 template <class T> cudaError_t launch_getindex(int ndim, const View<T>& v, const int* d_idx, int count, double* d_out, cudaStream_t s);
 template <class T> cudaError_t launch_measure(int ndim, bool perimeter, const View<T>& v, const double* h, double* d_partials, int nblocks, double* d_out, cudaStream_t s);
 template <class T> cudaError_t launch_signed_normals(int ndim, const View<T>& v, const double* h, double min_norm, const unsigned char* d_frozen, double band, T* a, long cstride, cudaStream_t s);
+// analytic generators (meshfield.jl:208-211 evaluated on the device): see lsm_field_fill_shape / lsm_field_fill_separable
+struct ShapeParams {
+    int shape, ndim, ncomp;
+    int n[3];                  // owned nodes
+    int first_last;            // global index of the first owned plane of the last dimension
+    double lc[3], h[3];
+    double p[8];               // shape parameters
+    long cstride;
+};
+cudaError_t launch_fill_shape(int f64, void* dst, const ShapeParams& P, cudaStream_t s);
+cudaError_t launch_fill_separable(int f64, void* dst, long cstride, const int* n, int ndim, const double* scale, const double* const (*tab)[3], cudaStream_t s);
 cudaError_t launch_csg(int f64, void* dst, const void* src, long n, int op, cudaStream_t s);
 cudaError_t launch_max_abs_diff(int f64, const void* a, const void* b, long n, unsigned long long* out, cudaStream_t s);
 

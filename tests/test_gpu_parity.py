@@ -373,6 +373,59 @@ def test_cfl_candidates_are_exact(m, O):
         assert outs[0][3]["d2h_bytes"] < outs[1][3]["d2h_bytes"]       # no 8-byte readback per step any more
 
 
+def test_device_generated_fields_match_numpy(m):
+    """lsm_field_fill_shape / lsm_field_fill_separable (MeshField(f, grid) for analytic f, meshfield.jl:208-211, evaluated on the
+    device) against the NumPy construction tests/helpers.py uses for the BASELINE configurations: bit for bit, both dtypes,
+    2-D and 3-D; the Zalesak disk of docs/src/example-zalesak.md:21-40 is assembled with the device set operations."""
+    for dtype in (np.float64, np.float32):
+        c3 = H.c3_enright(40, dtype)
+        g3 = c3.engine_grid(m)
+        sph = m.MeshField.from_shape(g3, "sphere", (0.35, 0.35, 0.35, 0.15), bc=m.NeumannBC(), dtype=dtype)
+        assert np.array_equal(sph.peek(), c3.phi0)
+        sc, tabs = H.enright_tables(c3.lc, c3.hc, c3.n)
+        vel = m.MeshField.from_separable(m.SeparableVelocity(g3, sc, tabs), dtype=dtype)
+        assert np.array_equal(vel.peek(), c3.terms[0]["field"].astype(dtype))
+        c5 = H.c5_normal_advection(24, dtype)
+        g5 = c5.engine_grid(m)
+        x, y, z = [c.ravel() for c in H.coords(c5.lc, c5.hc, c5.n)]
+        one = [np.ones_like(x), np.ones_like(y), np.ones_like(z)]
+        rot = m.SeparableVelocity(g5, (-1.0, 1.0, 0.0), [[one[0], y, one[2]], [x, one[1], one[2]], one])
+        assert np.array_equal(m.MeshField.from_separable(rot, dtype=dtype).peek(), c5.terms[1]["field"].astype(dtype))
+        assert np.array_equal(m.MeshField.from_shape(g5, "sphere", (0.3, 0.0, 0.0, 0.4), dtype=dtype).peek(), c5.phi0)
+        assert np.array_equal(m.MeshField.from_shape(g5, "const", (0.2,), dtype=dtype).peek(), c5.terms[0]["field"].astype(dtype))
+        cv = m.MeshField.from_shape(g5, "const", (0.5, -1.5, 2.0), dtype=dtype).peek()
+        assert cv.shape == (3, 24, 24, 24) and np.all(cv[0] == dtype(0.5)) and np.all(cv[1] == dtype(-1.5)) and np.all(cv[2] == dtype(2.0))
+        # 2-D: Zalesak = setdiff(disk, rec) with the reference's rectangle formula
+        c2 = H.c2_zalesak_curvature(96, dtype)
+        g2 = c2.engine_grid(m)
+        X, Y = H.coords(c2.lc, c2.hc, c2.n)
+        disk = m.MeshField.from_shape(g2, "sphere", (-0.75, 0.0, 0.5), bc=m.NeumannBC(), dtype=dtype)
+        assert np.array_equal(disk.peek(), (np.sqrt((X + 0.75) ** 2 + (Y - 0.0) ** 2) - 0.5).astype(dtype))
+        rec = m.MeshField.from_shape(g2, "box", (-0.75, -0.5, 0.2, 1.0), dtype=dtype)
+        rec_np = np.maximum(np.abs(X + 0.75) - 0.2 / 2, np.abs(Y + 0.5) - 1.0 / 2)
+        assert np.array_equal(rec.peek(), rec_np.astype(dtype))
+        zal = m.setdiff(disk, rec)
+        assert np.array_equal(zal.peek(), np.maximum(disk.peek(), -rec.peek()))
+        pl = m.MeshField.from_shape(g2, "plane", (0.6, -0.8, 0.1), dtype=dtype)
+        assert np.array_equal(pl.peek(), ((0.6 * X + -0.8 * Y) - 0.1).astype(dtype))
+    with pytest.raises(m.LSMError):
+        m.MeshField.from_shape(g2, "sphere", (0.0, 0.0), dtype=np.float64)          # wrong parameter count
+    # a device-generated state integrates like an uploaded one (no host array is ever created for it)
+    case = H.c3_enright(40)
+    g = case.engine_grid(m)
+    outs = []
+    for dev in (False, True):
+        phi = m.MeshField.from_shape(g, "sphere", (0.35, 0.35, 0.35, 0.15), bc=m.NeumannBC()) if dev else case.engine_field(m)
+        sc, tabs = H.enright_tables(case.lc, case.hc, case.n)
+        vel = m.MeshField.from_separable(m.SeparableVelocity(g, sc, tabs)) if dev else m.MeshField(case.terms[0]["field"], g)
+        eq = m.LevelSetEquation(terms=(m.AdvectionTerm(m.TimeScaled(vel, ("cos", 3.0)), m.WENO5()),), ic=phi, integrator=m.RK3())
+        if dev:
+            assert vel._vals is None
+        m.integrate(eq, 0.05)
+        outs.append((eq.t, eq.steps_taken, eq.state.peek().copy()))
+    assert outs[0][:2] == outs[1][:2] and np.array_equal(outs[0][2], outs[1][2])
+
+
 def test_against_committed_vectors(m):
     """The engine against tests/golden/oracle_vectors.npz (committed oracle outputs for small instances of C1..C5, f64 and
     f32): catches a change that moves the oracle and the engine together."""
