@@ -80,6 +80,9 @@ struct lsm_ctx {
     std::vector<CflCand> cfl_cand;
     int opt_cand = 1;           // LSM_OPT_CFL_CANDIDATES
     unsigned* d_cand_count = nullptr; double* d_cand = nullptr; double* h_cand = nullptr;   // candidate staging (device / pinned)
+    void* stage[2] = {nullptr, nullptr};        // AoS <-> SoA staging chunks of vector-field transfers (allocated on first use)
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    double* d_work = nullptr; size_t d_work_bytes = 0;     // persistent scratch of the reductions / getindex (grown on demand)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;     // pending stage timings
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t ev_user[8] = {};
@@ -191,6 +194,20 @@ void field_free(lsm_field* f) {
     delete f;
 }
 
+// persistent device scratch of the context (reductions, getindex): grown on demand, never freed per call
+int32_t ctx_scratch(lsm_ctx* c, size_t bytes, void** out) {
+    if (bytes > c->d_work_bytes) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->d_work) cudaFree(c->d_work);
+        c->d_work = nullptr; c->d_work_bytes = 0;
+        const size_t want = std::max<size_t>(bytes, 1u << 16);
+        CU(cudaMalloc(reinterpret_cast<void**>(&c->d_work), want));
+        c->d_work_bytes = want;
+    }
+    *out = c->d_work;
+    return LSM_OK;
+}
+
 int32_t ensure_buffers(lsm_field* phi, int nbuf) {
     lsm_field** slots[2] = {&phi->buf1, &phi->buf2};
     for (int b = 0; b < nbuf; ++b) {
@@ -287,11 +304,15 @@ int32_t exchange_halo(lsm_field* f, cudaStream_t s) {
     NC(nccl().GroupStart());
     // Every rank issues UPWARD traffic first, then DOWNWARD: NCCL matches the sends and receives of a pair of
     // ranks in issue order, and with 2 ranks and a periodic axis both directions join the same pair.
-    if (up >= 0)   { NC(nccl().Send(plane_ptr(top_first), bytes, ncclInt8, up, c->nccl_comm, s)); c->cnt.halo_bytes_sent += (int64_t)bytes; }
-    if (down >= 0) { NC(nccl().Recv(plane_ptr(-HALO), bytes, ncclInt8, down, c->nccl_comm, s)); }
-    if (down >= 0) { NC(nccl().Send(plane_ptr(bottom_first), bytes, ncclInt8, down, c->nccl_comm, s)); c->cnt.halo_bytes_sent += (int64_t)bytes; }
-    if (up >= 0)   { NC(nccl().Recv(plane_ptr(nl), bytes, ncclInt8, up, c->nccl_comm, s)); }
-    NC(nccl().GroupEnd());
+    // (a failing call still closes the group before the error is reported)
+    ncclResult_t gr = ncclSuccess;
+    auto keep = [&](ncclResult_t r) { if (gr == ncclSuccess) gr = r; };
+    if (up >= 0)   { keep(nccl().Send(plane_ptr(top_first), bytes, ncclInt8, up, c->nccl_comm, s)); c->cnt.halo_bytes_sent += (int64_t)bytes; }
+    if (down >= 0) { keep(nccl().Recv(plane_ptr(-HALO), bytes, ncclInt8, down, c->nccl_comm, s)); }
+    if (down >= 0) { keep(nccl().Send(plane_ptr(bottom_first), bytes, ncclInt8, down, c->nccl_comm, s)); c->cnt.halo_bytes_sent += (int64_t)bytes; }
+    if (up >= 0)   { keep(nccl().Recv(plane_ptr(nl), bytes, ncclInt8, up, c->nccl_comm, s)); }
+    keep(nccl().GroupEnd());
+    NC(gr);
     f->halo_valid = true;
     return LSM_OK;
 }
@@ -477,10 +498,11 @@ CflCand* cand_find(lsm_ctx* ctx, const lsm_term& t) {
     return nullptr;
 }
 
-bool cand_ready(lsm_ctx* ctx, const lsm_term& t) {
+// the candidate set answers (or is about to answer) this term's CFL requests: the fused in-kernel reduction is not needed
+bool cand_pending_or_ready(lsm_ctx* ctx, const lsm_term& t) {
     if (!ctx->opt_cand || !ctx->opt_cfl_cache || !t.field) return false;
     const CflCand* e = cand_find(ctx, t);
-    return e && e->built && !e->overflow && e->version == t.field->version;
+    return e && !e->overflow && e->version == t.field->version;
 }
 
 int32_t raw_cfl_pass(lsm_ctx* ctx, lsm_field* phi, const TermDev& td, unsigned long long* bits_out) {
@@ -747,6 +769,8 @@ int32_t lsm_ctx_destroy(lsm_ctx* c) {
     if (c->nccl_comm) nccl().CommDestroy(c->nccl_comm);
     if (c->d_scalar) cudaFree(c->d_scalar);
     if (c->h_scalar) cudaFreeHost(c->h_scalar);
+    for (int b = 0; b < 2; ++b) { if (c->stage[b]) cudaFree(c->stage[b]); if (c->ev_stage[b]) cudaEventDestroy(c->ev_stage[b]); if (c->ev_free[b]) cudaEventDestroy(c->ev_free[b]); }
+    if (c->d_work) cudaFree(c->d_work);
     if (c->d_cand) cudaFree(c->d_cand);
     if (c->d_cand_count) cudaFree(c->d_cand_count);
     if (c->h_cand) cudaFreeHost(c->h_cand);
@@ -934,15 +958,15 @@ int32_t lsm_field_getindex(lsm_field* f, const int32_t* I, int32_t count, double
         for (int d = 0; d < f->ndim; ++d)
             if ((I[t * f->ndim + d] < 1 || I[t * f->ndim + d] > f->n[d]) && !f->has_bc)
                 return fail(LSM_ERR_BC, "index lies outside the grid, but the field has no boundary conditions to resolve it");
-    int* d_idx = nullptr; double* d_out = nullptr;
-    CU(cudaMalloc(&d_idx, sizeof(int) * (size_t)count * f->ndim));
-    cudaError_t e = cudaMalloc(&d_out, sizeof(double) * (size_t)count);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, I, sizeof(int) * (size_t)count * f->ndim, cudaMemcpyHostToDevice, c->stream);
+    void* work = nullptr;
+    TRY(ctx_scratch(c, sizeof(double) * (size_t)count + sizeof(int) * (size_t)count * f->ndim, &work));
+    double* d_out = static_cast<double*>(work);
+    int* d_idx = reinterpret_cast<int*>(d_out + count);
+    cudaError_t e = cudaMemcpyAsync(d_idx, I, sizeof(int) * (size_t)count * f->ndim, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = f->dtype == LSM_F64 ? launch_getindex<double>(f->ndim, make_view<double>(f), d_idx, count, d_out, c->stream)
                                                   : launch_getindex<float>(f->ndim, make_view<float>(f), d_idx, count, d_out, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_idx); if (d_out) cudaFree(d_out);
     if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "getindex failed: %s", cudaGetErrorString(e));
     c->cnt.kernel_launches += 1;
     return LSM_OK;
@@ -957,6 +981,51 @@ int32_t lsm_field_stage_buffer(lsm_field* phi, int32_t which, lsm_field** out) {
     return LSM_OK;
 }
 
+// Vector fields are AoS on the host (Array{SVector{N,T},N}) and SoA on the device.  The transfer runs in chunks through two
+// persistent 32 MB staging buffers: the copy engine moves chunk k+1 on the comm stream while the transpose kernel handles chunk k
+// on the compute stream — no second full-size allocation (a 1024^3 Float64 velocity is 25.8 GB) and no cudaMalloc per call.
+constexpr size_t STAGE_BYTES = 32u << 20;
+
+int32_t staged_vector_transfer(lsm_field* f, void* host, bool upload) {
+    lsm_ctx* c = f->ctx;
+    const size_t es = esize(f->dtype);
+    for (int b = 0; b < 2; ++b) {
+        if (!c->stage[b]) CU(cudaMalloc(&c->stage[b], STAGE_BYTES));
+        if (!c->ev_stage[b]) CU(cudaEventCreateWithFlags(&c->ev_stage[b], cudaEventDisableTiming));
+        if (!c->ev_free[b]) CU(cudaEventCreateWithFlags(&c->ev_free[b], cudaEventDisableTiming));
+    }
+    const long chunk = (long)(STAGE_BYTES / (es * f->ncomp));
+    char* hp = static_cast<char*>(host);
+    char* dp = static_cast<char*>(f->p);
+    int k = 0;
+    for (long a = 0; a < f->owned; a += chunk, ++k) {
+        const int b = k & 1;
+        const long n = std::min(chunk, f->owned - a);
+        const size_t hb = (size_t)n * f->ncomp * es;
+        cudaError_t e;
+        if (upload) {
+            CU(cudaStreamWaitEvent(c->comm, c->ev_free[b], 0));                  // the transpose of chunk k-2 has drained this buffer
+            CU(cudaMemcpyAsync(c->stage[b], hp + (size_t)a * f->ncomp * es, hb, cudaMemcpyHostToDevice, c->comm));
+            CU(cudaEventRecord(c->ev_stage[b], c->comm));
+            CU(cudaStreamWaitEvent(c->stream, c->ev_stage[b], 0));
+            e = launch_transpose(f->dtype == LSM_F64, true, c->stage[b], dp + (size_t)a * es, n, f->ncomp, f->cstride, c->stream);
+            CU(cudaEventRecord(c->ev_free[b], c->stream));
+        } else {
+            CU(cudaStreamWaitEvent(c->stream, c->ev_free[b], 0));                // the D2H of chunk k-2 has drained this buffer
+            e = launch_transpose(f->dtype == LSM_F64, false, dp + (size_t)a * es, c->stage[b], n, f->ncomp, f->cstride, c->stream);
+            CU(cudaEventRecord(c->ev_stage[b], c->stream));
+            CU(cudaStreamWaitEvent(c->comm, c->ev_stage[b], 0));
+            CU(cudaMemcpyAsync(hp + (size_t)a * f->ncomp * es, c->stage[b], hb, cudaMemcpyDeviceToHost, c->comm));
+            CU(cudaEventRecord(c->ev_free[b], c->comm));
+        }
+        if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "transpose kernel launch failed: %s", cudaGetErrorString(e));
+        c->cnt.kernel_launches += 1;
+    }
+    CU(cudaStreamSynchronize(c->comm));
+    CU(cudaStreamSynchronize(c->stream));
+    return LSM_OK;
+}
+
 int32_t lsm_field_upload(lsm_field* f, const void* host) {
     if (!f || !host) return fail(LSM_ERR_ARG, "null argument");
     if (f->separable) return fail(LSM_ERR_ARG, "separable fields have no dense storage");
@@ -965,17 +1034,11 @@ int32_t lsm_field_upload(lsm_field* f, const void* host) {
     const size_t bytes = (size_t)f->owned * f->ncomp * esize(f->dtype);
     if (f->ncomp == 1) {
         CU(cudaMemcpyAsync(f->p, host, bytes, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
     } else {
-        void* stage = nullptr;
-        CU(cudaMalloc(&stage, bytes));
-        cudaError_t e = cudaMemcpyAsync(stage, host, bytes, cudaMemcpyHostToDevice, c->stream);
-        if (e == cudaSuccess) e = launch_transpose(f->dtype == LSM_F64, true, stage, f->p, f->owned, f->ncomp, f->cstride, c->stream);
-        cudaStreamSynchronize(c->stream);
-        cudaFree(stage);
-        if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
-        c->cnt.kernel_launches += 1;
+        CU(cudaStreamSynchronize(c->comm));
+        TRY(staged_vector_transfer(f, const_cast<void*>(host), true));
     }
-    CU(cudaStreamSynchronize(c->stream));
     c->cnt.h2d_bytes += (int64_t)bytes;
     f->version++; f->halo_valid = false;
     return LSM_OK;
@@ -990,17 +1053,10 @@ int32_t lsm_field_download(lsm_field* f, void* host) {
     const size_t bytes = (size_t)f->owned * f->ncomp * esize(f->dtype);
     if (f->ncomp == 1) {
         CU(cudaMemcpyAsync(host, f->p, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
     } else {
-        void* stage = nullptr;
-        CU(cudaMalloc(&stage, bytes));
-        cudaError_t e = launch_transpose(f->dtype == LSM_F64, false, f->p, stage, f->owned, f->ncomp, f->cstride, c->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(host, stage, bytes, cudaMemcpyDeviceToHost, c->stream);
-        cudaStreamSynchronize(c->stream);
-        cudaFree(stage);
-        if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "download failed: %s", cudaGetErrorString(e));
-        c->cnt.kernel_launches += 1;
+        TRY(staged_vector_transfer(f, host, false));
     }
-    CU(cudaStreamSynchronize(c->stream));
     c->cnt.d2h_bytes += (int64_t)bytes;
     return LSM_OK;
 }
@@ -1091,7 +1147,7 @@ int32_t lsm_integrate(lsm_ctx* ctx, int32_t integrator, double cfl, lsm_field* p
         for (int s = 1; s <= nstages(integrator) && rc == LSM_OK; ++s) {
             if (s == nstages(integrator) && ctx->opt_fuse_cfl && ctx->opt_cfl_cache && nterms == 1 && terms[0].kind == LSM_TERM_ADVECTION &&
                 (terms[0].coef_kind == LSM_COEF_FIELD || terms[0].coef_kind == LSM_COEF_SEPARABLE) && terms[0].tscale_kind == LSM_TS_COS && (tc + dt) <= tf - jl_eps(tc + dt) &&
-                !(ctx->opt_cand && cand_find(ctx, terms[0]) && !cand_find(ctx, terms[0])->overflow && cand_find(ctx, terms[0])->version == terms[0].field->version)) {
+                !cand_pending_or_ready(ctx, terms[0])) {
                 // next step's CFL maximum from this stage's velocity traffic: max(g') >= (1 - 1e-13) * max(g) * |g'/g|
                 for (const auto& en : ctx->cfl_cache)
                     if (en.kind == terms[0].kind && en.field == terms[0].field && en.version == terms[0].field->version && en.scaled && en.g != 0.0) {
@@ -1127,6 +1183,7 @@ int32_t lsm_integrate(lsm_ctx* ctx, int32_t integrator, double cfl, lsm_field* p
         tc += dt;
         ++steps;
     }
+    ctx->fuse_req.on = false;        // a request left behind by a failed stage must not leak into a later lsm_stage
     if (gexec) { cudaStreamSynchronize(ctx->stream); cudaGraphExecDestroy(gexec); }
     cudaStreamSynchronize(ctx->comm);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -1159,8 +1216,9 @@ static int32_t measure_impl(lsm_ctx* ctx, lsm_field* phi, bool perimeter, double
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->comm));
     const int nblocks = ctx->sm_count * 8;
-    double* d_part = nullptr;
-    CU(cudaMalloc(&d_part, sizeof(double) * (size_t)(nblocks + 1)));
+    void* work = nullptr;
+    TRY(ctx_scratch(ctx, sizeof(double) * (size_t)(nblocks + 1), &work));      // persistent: a posthook payload must not cudaMalloc per call
+    double* d_part = static_cast<double*>(work);
     cudaError_t e;
     // perimeter reaches off-grid at the border: a field without BCs gets LinearExtrapolationBC (levelsetops.jl:142)
     lsm_bc saved[3][2];
@@ -1169,18 +1227,17 @@ static int32_t measure_impl(lsm_ctx* ctx, lsm_field* phi, bool perimeter, double
     if (perimeter && !had_bc) for (int d = 0; d < phi->ndim; ++d) { phi->bc[d][0] = {LSM_BC_EXTRAP, 1}; phi->bc[d][1] = {LSM_BC_EXTRAP, 1}; }
     if (perimeter && ctx->nranks > 1 && !phi->halo_valid) {
         int32_t rc = exchange_halo(phi, ctx->stream);
-        if (rc != LSM_OK) { cudaFree(d_part); return rc; }
+        if (rc != LSM_OK) return rc;
     }
     if (phi->dtype == LSM_F64) e = launch_measure<double>(phi->ndim, perimeter, make_view<double>(phi), phi->h, d_part, nblocks, d_part + nblocks, ctx->stream);
     else e = launch_measure<float>(phi->ndim, perimeter, make_view<float>(phi), phi->h, d_part, nblocks, d_part + nblocks, ctx->stream);
     std::memcpy(phi->bc, saved, sizeof saved);
     if (e == cudaSuccess && ctx->nranks > 1) {
         ncclResult_t r = nccl().AllReduce(d_part + nblocks, d_part + nblocks, 1, ncclDouble, ncclSum, ctx->nccl_comm, ctx->stream);
-        if (r != ncclSuccess) { cudaFree(d_part); return fail(LSM_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString(r)); }
+        if (r != ncclSuccess) return fail(LSM_ERR_NCCL, "ncclAllReduce failed: %s", nccl().GetErrorString(r));
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_part + nblocks, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_part);
     if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "measure kernel failed: %s", cudaGetErrorString(e));
     ctx->cnt.kernel_launches += 2; ctx->cnt.d2h_bytes += 8;
     return LSM_OK;

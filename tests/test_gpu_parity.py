@@ -763,27 +763,35 @@ def test_graph_replay_is_invisible(m, O):
 
 @pytest.mark.parametrize("integ", ["RK3", "RK2", "FE"])
 def test_counters_and_launch_accounting(m, integ):
-    """Launch accounting and the fused next-step CFL (exact, so states are bit-identical with the option off) for all three
-    integrators: the last stage of each runs its own fused-CFL instantiation (RK3 S3, RK2 corrector, ForwardEuler)."""
+    """Launch accounting of the three ways the per-step CFL maximum of a time-scaled velocity is obtained, for all three
+    integrators (all exact, so the states are bit-identical): (a) default — host evaluation over the candidate nodes: one
+    reduction for the first step, the unscaled reduction + one extraction kernel when the set is built, nothing afterwards;
+    (b) candidates off — the last stage of every step reduces the next step's maximum (fused-CFL instantiations: RK3 S3,
+    RK2 corrector, ForwardEuler); (c) both off — one reduction pass per step."""
     ctx = m.default_context()
     case = H.c3_enright(32)
     mk, nst = {"RK3": (m.RK3, 3), "RK2": (m.RK2, 2), "FE": (m.ForwardEuler, 1)}[integ]
     results = []
-    for fuse in (0, 1):
+    for cand, fuse in ((1, 1), (0, 1), (0, 0)):
+        ctx.set_option(m._lib.OPT_CFL_CANDIDATES, cand)
         ctx.set_option(m._lib.OPT_FUSE_CFL, fuse)
         phi = case.engine_field(m)
         eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=mk())
         eq.state.device()
-        eq.terms[0].velocity.base.device()            # upload the coefficient (one AoS->SoA kernel) before counting
+        eq.terms[0].velocity.base.device()            # upload the coefficient (AoS->SoA kernels) before counting
         ctx.reset_counters()
         m.integrate(eq, 0.02)
         c = ctx.counters()
+        assert eq.steps_taken >= 3
         assert c["stage_launches"] == nst * eq.steps_taken
-        # cos(pi t/T) changes every step: one CFL reduction per step, unless the last RK stage of the previous step
-        # already produced it (fused CFL) — then only the very first step needs a separate pass
-        assert c["cfl_passes"] == (1 if fuse else eq.steps_taken)
-        assert c["kernel_launches"] == c["stage_launches"] + c["cfl_passes"]
+        if cand:
+            assert c["cfl_passes"] == 2 and c["kernel_launches"] == c["stage_launches"] + 3
+        else:
+            assert c["cfl_passes"] == (1 if fuse else eq.steps_taken)
+            assert c["kernel_launches"] == c["stage_launches"] + c["cfl_passes"]
         results.append((eq.t, eq.steps_taken, eq.state.peek().copy()))
     ctx.set_option(m._lib.OPT_FUSE_CFL, 1)
+    ctx.set_option(m._lib.OPT_CFL_CANDIDATES, 1)
+    assert results[0][:2] == results[2][:2] and np.array_equal(results[0][2], results[2][2])
     # the fused reduction is exact: identical step sizes, hence bit-identical states
     assert results[0][:2] == results[1][:2] and np.array_equal(results[0][2], results[1][2])
