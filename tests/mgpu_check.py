@@ -116,6 +116,7 @@ def main():
     if rank == 0:
         c = ctx.counters()
         print(f"halo bytes sent by rank 0: {c['halo_bytes_sent']}", flush=True)
+        print("ALL OK" if res[0] else "FAILED", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if res[0] else 1)
 
