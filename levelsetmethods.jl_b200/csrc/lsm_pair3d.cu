@@ -132,9 +132,68 @@ __device__ __forceinline__ void pair_eval(const WenoK& K, const T (&a)[7], const
     }
 }
 
+// The same evaluation on first differences d0..d4 AND their differences e1..e4 computed by the caller (so that other terms can
+// share them).  Float64 only.
+template <bool XMAX>
+__device__ __forceinline__ double weno_core_de(const WenoK& K, double d0, double d1, double d2, double d3, double d4,
+                                               double e1, double e2, double e3, double e4) {
+    const double m = XMAX ? absmax5(d0, d1, d2, d3, d4) : absmax5_hi(d0, d1, d2, d3, d4);
+    const double eps = fma(K.e6, m * m, K.fl);
+    const double c133 = K.c133;
+    const double t1a = e2 - e1, t1b = e3 - e2, t1c = e4 - e3;
+    const double t2a = fma(3.0, e2, -e1), t2b = e2 + e3, t2c = fma(-3.0, e3, e4);
+    const double b1 = fma(t2a, t2a, fma(c133, t1a * t1a, eps));
+    const double b2 = fma(t2b, t2b, fma(c133, t1b * t1b, eps));
+    const double b3 = fma(t2c, t2c, fma(c133, t1c * t1c, eps));
+    const double p12 = b1 * b2, p13 = b1 * b3, p23 = b2 * b3;
+    const double w1 = p23 * p23, w2 = p13 * p13, w3 = p12 * p12;
+    const double den = fma(3.0, w3, fma(6.0, w2, w1));
+    const double G1 = fma(K.c56, e2, K.cm13 * e1);
+    const double G2 = fma(2.0, e3, e2);
+    const double G3 = fma(2.0, e3, -0.5 * e4);
+    const double num = fma(w3, G3, fma(w2, G2, w1 * G1));
+    return fma(num, fast_rcp<1>(den), d2);
+}
+
+// One dimension of "NormalMotionTerm + AdvectionTerm(WENO5)" (BASELINE config 5) for two nodes.  The six first differences
+// D[k] = phi[k-2] - phi[k-3] and five second differences E[k] = D[k+1] - D[k] of a node feed BOTH terms:
+//   * the second-order ENO pair of the Godunov norm (levelsetterms.jl:156-170): D-  = D[2], D+ = D[3], D2-- = E[1], D20 = E[2],
+//     D2++ = E[3] (undivided; the reference forms D20 = (phi+ - 2 phi0 + phi-)/h^2 directly, this is the same value up to rounding);
+//   * WENO5 on D[0..4] (minus-biased) or D[5..1] with negated E (plus-biased).
+// sp = (speed > 0) selects grad+ / grad-; g accumulates the selected squares (times w = 1/h_d^2 unless the mesh is isotropic).
+template <bool XMAX, bool ISO>
+__device__ __forceinline__ void pair_eval_n(const WenoK& K, const double (&a)[7], const double (&b)[7], int xa, int xb, bool spa, bool spb,
+                                            double w, double& WA, double& WB, double& ga, double& gb) {
+    double DA[6], DB[6], EA[5], EB[5];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { DA[k] = a[k + 1] - a[k]; DB[k] = b[k + 1] - b[k]; }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { EA[k] = DA[k + 1] - DA[k]; EB[k] = DB[k + 1] - DB[k]; }
+    {
+        const double nga = fma(0.5, minmod(EA[1], EA[2]), DA[2]), psa = fma(-0.5, minmod(EA[3], EA[2]), DA[3]);
+        const double ngb = fma(0.5, minmod(EB[1], EB[2]), DB[2]), psb = fma(-0.5, minmod(EB[3], EB[2]), DB[3]);
+        const double a1 = ((nga > 0) == spa) ? nga : 0.0, a2 = ((psa < 0) == spa) ? psa : 0.0;
+        const double b1 = ((ngb > 0) == spb) ? ngb : 0.0, b2 = ((psb < 0) == spb) ? psb : 0.0;
+        if (ISO) { ga = fma(a1, a1, fma(a2, a2, ga)); gb = fma(b1, b1, fma(b2, b2, gb)); }
+        else { ga = fma(fma(a1, a1, a2 * a2), w, ga); gb = fma(fma(b1, b1, b2 * b2), w, gb); }
+    }
+    if ((xa | xb) >= 0) {
+        WA = weno_core_de<XMAX>(K, DA[0], DA[1], DA[2], DA[3], DA[4], EA[0], EA[1], EA[2], EA[3]);
+        WB = weno_core_de<XMAX>(K, DB[0], DB[1], DB[2], DB[3], DB[4], EB[0], EB[1], EB[2], EB[3]);
+    } else if ((xa & xb) < 0) {
+        WA = weno_core_de<XMAX>(K, DA[5], DA[4], DA[3], DA[2], DA[1], -EA[4], -EA[3], -EA[2], -EA[1]);
+        WB = weno_core_de<XMAX>(K, DB[5], DB[4], DB[3], DB[2], DB[1], -EB[4], -EB[3], -EB[2], -EB[1]);
+    } else {
+        WA = xa >= 0 ? weno_core_de<XMAX>(K, DA[0], DA[1], DA[2], DA[3], DA[4], EA[0], EA[1], EA[2], EA[3])
+                     : weno_core_de<XMAX>(K, DA[5], DA[4], DA[3], DA[2], DA[1], -EA[4], -EA[3], -EA[2], -EA[1]);
+        WB = xb >= 0 ? weno_core_de<XMAX>(K, DB[0], DB[1], DB[2], DB[3], DB[4], EB[0], EB[1], EB[2], EB[3])
+                     : weno_core_de<XMAX>(K, DB[5], DB[4], DB[3], DB[2], DB[1], -EB[4], -EB[3], -EB[2], -EB[1]);
+    }
+}
+
 // CK: COEF_FIELD (stored velocity, staged by TMA next to the phi ring) or COEF_SEPARABLE (u_d = s_d X_d[i] Y_d[j] Z_d[k] from tables).
 // SB: static RK base mode (SB_* of lsm_tile_util.cuh).  FCFL: also reduce the next step's CFL maximum (see StageParams).
-template <class T, int RY, int NT, int CK, bool FCFL, int SB, bool ISO, bool XMAX>
+template <class T, int RY, int NT, int CK, bool FCFL, int SB, bool ISO, bool XMAX, bool HASN>
 __global__ void __launch_bounds__(NT, 2)
 pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ AuxList A, const __grid_constant__ TmaMaps M, const int cz) {
     using G = PairGeom<T, RY, NT>;
@@ -142,8 +201,13 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
     constexpr int RING = G::RING, W = G::W, PLANE = G::PLANE, TILE = G::TILE;
     constexpr bool HAS_P0 = SB == SB_S2 || SB == SB_S3 || SB == SB_P0;
     constexpr bool HAS_OUT2 = SB == SB_IN_OUT2;
-    constexpr int NVEL = CK == COEF_FIELD ? 3 : 0;
+    // HASN: the term list is (NormalMotionTerm(stored speed), AdvectionTerm(stored velocity, WENO5)) — BASELINE config 5; else the
+    // single advection term.  Aux tiles: [speed,] u1, u2, u3 [, phi^n]
+    constexpr int TA = HASN ? 1 : 0;                       // index of the advection term
+    constexpr int AU = HASN ? 1 : 0;                       // first velocity tile
+    constexpr int NVEL = (CK == COEF_FIELD ? 3 : 0) + AU;  // tiles before phi^n
     constexpr int NAUX = NVEL + (HAS_P0 ? 1 : 0);
+    static_assert(!HASN || (CK == COEF_FIELD && !FCFL && sizeof(T) == 8 && RY == 1), "the two-term variant is Float64, stored coefficients");
     constexpr unsigned PHI_BYTES = (unsigned)(W * G::HH * sizeof(T));
     constexpr unsigned AUX_BYTES = (unsigned)(NAUX * TILE * sizeof(T));
 
@@ -223,13 +287,16 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
     bool act[RY];
 #pragma unroll
     for (int r = 0; r < RY; ++r) act[r] = i < n0 && (j0 + r) < n1;
-    const double g = P.terms[0].scaled ? P.terms[0].g : 1.0;
+    const double g = P.terms[TA].scaled ? P.terms[TA].g : 1.0;
+    const double gN = HASN && P.terms[0].scaled ? P.terms[0].g : 1.0;
+    const double ihsq[3] = {(1.0 / P.h[0]) * (1.0 / P.h[0]), (1.0 / P.h[1]) * (1.0 / P.h[1]), (1.0 / P.h[2]) * (1.0 / P.h[2])};
     const int ghi = __double2hiint(g);
     const double gih[3] = {g * (1.0 / P.h[0]), g * (1.0 / P.h[1]), g * (1.0 / P.h[2])};
     // ISO (equal mesh size in the three dimensions, the usual case): sum_d (u_d g / h) W_d = (g / h) sum_d u_d W_d, so the per-
     // dimension scaling (3 DMUL per node) folds into the stage coefficient: x -= (c g / h) * sum_d u_d W_d.
     const double tau = ISO ? P.cfl_tau / fabs(gih[0]) * (1.0 - 1e-15) : P.cfl_tau;      // candidate bound on the unscaled estimate (ISO)
     const double cH = ISO ? P.c * gih[0] : P.c, cH2 = ISO ? P.c2 * gih[0] : P.c2;
+    const double cN = ISO ? P.c * (1.0 / P.h[0]) : P.c, cN2 = ISO ? P.c2 * (1.0 / P.h[0]) : P.c2;     // normal term: sqrt(sum / h^2) = sqrt(sum) / h
     auto scl = [&](double u, int d) -> double { return ISO ? u : u * gih[d]; };
     // separable velocity: the x-y factor of every node is a loop invariant (same product order as the stored tables)
     double pxy[RY][2][3];
@@ -240,7 +307,7 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
             for (int c = 0; c < 2; ++c) {
                 const int ii = min(i + c, n0 - 1), jj = min(j0 + r, n1 - 1);
 #pragma unroll
-                for (int d = 0; d < 3; ++d) pxy[r][c][d] = (P.terms[0].cval[d] * __ldg(P.terms[0].tab[d][0] + ii)) * __ldg(P.terms[0].tab[d][1] + jj);
+                for (int d = 0; d < 3; ++d) pxy[r][c][d] = (P.terms[TA].cval[d] * __ldg(P.terms[TA].tab[d][0] + ii)) * __ldg(P.terms[TA].tab[d][1] + jj);
             }
     }
     // The five WENO constants that do not fit an instruction immediate are made opaque to ptxas (threadIdx.z is always 0, which
@@ -294,6 +361,29 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
             double H[RY][2];
             double uraw[RY][2][3];
             V2 cc[RY];
+            // normal-motion term (HASN): speed of the two nodes, which Godunov norm it selects, and the accumulated squares
+            double vn[RY][2], gn[RY][2];
+            bool sp[RY][2];
+#pragma unroll
+            for (int r = 0; r < RY; ++r) {
+                if (HASN) {
+                    const V2 vv = lds_pair(auxz + r * G::BX * ES, T());
+                    vn[r][0] = double(vv.x) * gN; vn[r][1] = double(vv.y) * gN;
+                    if (!P.terms[0].scaled) { vn[r][0] = double(vv.x); vn[r][1] = double(vv.y); }
+                } else { vn[r][0] = vn[r][1] = 0.0; }
+                sp[r][0] = vn[r][0] > 0; sp[r][1] = vn[r][1] > 0;
+                gn[r][0] = gn[r][1] = 0.0;
+            }
+            // one dimension for the pair (a, b): the single-term evaluation, or the shared-difference two-term one
+            auto evalp = [&](const T (&a)[7], const T (&b)[7], double ua, double ub, int d, int r, double& wa, double& wb) {
+                if constexpr (HASN) {
+                    const double ad[7] = {double(a[0]), double(a[1]), double(a[2]), double(a[3]), double(a[4]), double(a[5]), double(a[6])};
+                    const double bd[7] = {double(b[0]), double(b[1]), double(b[2]), double(b[3]), double(b[4]), double(b[5]), double(b[6])};
+                    pair_eval_n<XMAX, ISO>(KR, ad, bd, __double2hiint(ua) ^ ghi, __double2hiint(ub) ^ ghi, sp[r][0], sp[r][1], ihsq[d], wa, wb, gn[r][0], gn[r][1]);
+                } else {
+                    pair_eval<T, XMAX>(KR, a, b, __double2hiint(ua) ^ ghi, __double2hiint(ub) ^ ghi, wa, wb);
+                }
+            };
             // ---- x: the two nodes of a row share 6 of their 7 samples
 #pragma unroll
             for (int r = 0; r < RY; ++r) {
@@ -305,12 +395,12 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
                 const T b[7] = {m1.x, m1.y, c0.x, c0.y, p1.x, p1.y, p2.x};
                 double ua, ub;
                 if (CK == COEF_FIELD) {
-                    const V2 u = lds_pair(auxz + r * G::BX * ES, T());
+                    const V2 u = lds_pair(auxz + (AU * TILE + r * G::BX) * ES, T());
                     ua = double(u.x); ub = double(u.y);
-                } else { ua = pxy[r][0][0] * __ldg(P.terms[0].tab[0][2] + z); ub = pxy[r][1][0] * __ldg(P.terms[0].tab[0][2] + z); }
+                } else { ua = pxy[r][0][0] * __ldg(P.terms[TA].tab[0][2] + z); ub = pxy[r][1][0] * __ldg(P.terms[TA].tab[0][2] + z); }
                 uraw[r][0][0] = ua; uraw[r][1][0] = ub;
                 double wa, wb;
-                pair_eval<T, XMAX>(KR, a, b, __double2hiint(ua) ^ ghi, __double2hiint(ub) ^ ghi, wa, wb);
+                evalp(a, b, ua, ub, 0, r, wa, wb);
                 H[r][0] = scl(ua, 0) * wa;
                 H[r][1] = scl(ub, 0) * wb;
             }
@@ -323,16 +413,16 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
 #pragma unroll
                 for (int r = 0; r < RY; ++r) {
                     if (CK == COEF_FIELD) {
-                        const V2 uu = lds_pair(auxz + (TILE + r * G::BX) * ES, T());
+                        const V2 uu = lds_pair(auxz + ((AU + 1) * TILE + r * G::BX) * ES, T());
                         u[r][0] = double(uu.x); u[r][1] = double(uu.y);
-                    } else { u[r][0] = pxy[r][0][1] * __ldg(P.terms[0].tab[1][2] + z); u[r][1] = pxy[r][1][1] * __ldg(P.terms[0].tab[1][2] + z); }
+                    } else { u[r][0] = pxy[r][0][1] * __ldg(P.terms[TA].tab[1][2] + z); u[r][1] = pxy[r][1][1] * __ldg(P.terms[TA].tab[1][2] + z); }
                     uraw[r][0][1] = u[r][0]; uraw[r][1][1] = u[r][1];
                 }
                 if (RY == 1) {
                     const T a[7] = {yv[0].x, yv[1].x, yv[2].x, yv[3].x, yv[4].x, yv[5].x, yv[6].x};
                     const T b[7] = {yv[0].y, yv[1].y, yv[2].y, yv[3].y, yv[4].y, yv[5].y, yv[6].y};
                     double wa, wb;
-                    pair_eval<T, XMAX>(KR, a, b, __double2hiint(u[0][0]) ^ ghi, __double2hiint(u[0][1]) ^ ghi, wa, wb);
+                    evalp(a, b, u[0][0], u[0][1], 1, 0, wa, wb);
                     H[0][0] = fma(scl(u[0][0], 1), wa, H[0][0]);
                     H[0][1] = fma(scl(u[0][1], 1), wb, H[0][1]);
                 } else {
@@ -360,12 +450,12 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
                 const T b[7] = {zv[0].y, zv[1].y, zv[2].y, zv[3].y, zv[4].y, zv[5].y, zv[6].y};
                 double ua, ub;
                 if (CK == COEF_FIELD) {
-                    const V2 u = lds_pair(auxz + (2 * TILE + r * G::BX) * ES, T());
+                    const V2 u = lds_pair(auxz + ((AU + 2) * TILE + r * G::BX) * ES, T());
                     ua = double(u.x); ub = double(u.y);
-                } else { ua = pxy[r][0][2] * __ldg(P.terms[0].tab[2][2] + z); ub = pxy[r][1][2] * __ldg(P.terms[0].tab[2][2] + z); }
+                } else { ua = pxy[r][0][2] * __ldg(P.terms[TA].tab[2][2] + z); ub = pxy[r][1][2] * __ldg(P.terms[TA].tab[2][2] + z); }
                 uraw[r][0][2] = ua; uraw[r][1][2] = ub;
                 double wa, wb;
-                pair_eval<T, XMAX>(KR, a, b, __double2hiint(ua) ^ ghi, __double2hiint(ub) ^ ghi, wa, wb);
+                evalp(a, b, ua, ub, 2, r, wa, wb);
                 H[r][0] = fma(scl(ua, 2), wa, H[r][0]);
                 H[r][1] = fma(scl(ub, 2), wb, H[r][1]);
             }
@@ -384,14 +474,27 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
                         else xb[c] = pv[c];                                                                // RK2 S2 (corr)
                     }
                 }
+                // terms are subtracted one after the other with a rounding to the storage type in between, like the reference
+                // (x = base; x -= c H_normal; x -= c H_advection, timestepping.jl:128-202)
+                T x2[2] = {cc[r].x, cc[r].y};
+                if (HASN) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        // positive(v) sqrt(grad+) + negative(v) sqrt(grad-): one of the two products is exactly 0; a NaN speed gives 0
+                        const double v = vn[r][c];
+                        const double hn = (v > 0 ? v : (v < 0 ? v : 0.0)) * sqrt(gn[r][c]);
+                        xb[c] = T(fma(-cN, hn, double(xb[c])));
+                        if (HAS_OUT2) x2[c] = T(fma(-cN2, hn, double(x2[c])));
+                    }
+                }
                 V2 o;
                 o.x = T(fma(-cH, H[r][0], double(xb[0])));
                 o.y = T(fma(-cH, H[r][1], double(xb[1])));
                 *reinterpret_cast<V2*>(P.out + lin + r * vs1) = o;
                 if (HAS_OUT2) {
                     V2 o2;
-                    o2.x = T(fma(-cH2, H[r][0], double(cc[r].x)));
-                    o2.y = T(fma(-cH2, H[r][1], double(cc[r].y)));
+                    o2.x = T(fma(-cH2, H[r][0], double(x2[0])));
+                    o2.y = T(fma(-cH2, H[r][1], double(x2[1])));
                     *reinterpret_cast<V2*>(P.out2 + lin + r * vs1) = o2;
                 }
                 if (FCFL) {
@@ -448,13 +551,13 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
 #define LSM_PAIR_NT 256
 #endif
 
-template <class T, int CK, bool FCFL, int SB, bool ISO, bool XMAX>
+template <class T, int CK, bool FCFL, int SB, bool ISO, bool XMAX, bool HASN = false>
 cudaError_t launch_pair_x(const StageParams<T>& P, const AuxList& A, cudaStream_t s) {
     constexpr int RY = LSM_PAIR_RY, NT = LSM_PAIR_NT;
     using G = PairGeom<T, RY, NT>;
-    auto kern = pair3d_kernel<T, RY, NT, CK, FCFL, SB, ISO, XMAX>;
+    auto kern = pair3d_kernel<T, RY, NT, CK, FCFL, SB, ISO, XMAX, HASN>;
     constexpr bool HAS_P0 = SB == SB_S2 || SB == SB_S3 || SB == SB_P0;
-    constexpr int NAUX = (CK == COEF_FIELD ? 3 : 0) + (HAS_P0 ? 1 : 0);
+    constexpr int NAUX = (CK == COEF_FIELD ? 3 : 0) + (HASN ? 1 : 0) + (HAS_P0 ? 1 : 0);
     const size_t smem = G::smem_bytes(NAUX);
     static size_t attr_smem[16] = {};
     { cudaError_t e = ensure_dyn_smem(kern, smem, attr_smem); if (e != cudaSuccess) return e; }
@@ -472,27 +575,27 @@ cudaError_t launch_pair_x(const StageParams<T>& P, const AuxList& A, cudaStream_
     return cudaGetLastError();
 }
 
-template <class T, int CK, bool FCFL, int SB>
+template <class T, int CK, bool FCFL, int SB, bool HASN>
 cudaError_t launch_pair(const StageParams<T>& P, const AuxList& A, cudaStream_t s, bool exact_eps) {
     const bool iso = P.h[0] == P.h[1] && P.h[1] == P.h[2];
     if (sizeof(T) == 4 || !exact_eps)      // (the Float32 evaluation normalises by the exact FP32 maximum either way)
-        return iso ? launch_pair_x<T, CK, FCFL, SB, true, false>(P, A, s) : launch_pair_x<T, CK, FCFL, SB, false, false>(P, A, s);
+        return iso ? launch_pair_x<T, CK, FCFL, SB, true, false, HASN>(P, A, s) : launch_pair_x<T, CK, FCFL, SB, false, false, HASN>(P, A, s);
     if constexpr (sizeof(T) == 8)
-        return iso ? launch_pair_x<T, CK, FCFL, SB, true, true>(P, A, s) : launch_pair_x<T, CK, FCFL, SB, false, true>(P, A, s);
+        return iso ? launch_pair_x<T, CK, FCFL, SB, true, true, HASN>(P, A, s) : launch_pair_x<T, CK, FCFL, SB, false, true, HASN>(P, A, s);
     return cudaErrorNotSupported;
 }
 
-template <class T, int CK, bool FCFL>
+template <class T, int CK, bool FCFL, bool HASN = false>
 cudaError_t launch_pair_sb(const StageParams<T>& P, const AuxList& A, cudaStream_t s, bool exact_eps) {
-    constexpr int SP0 = CK == COEF_FIELD ? 3 : 0;
+    constexpr int SP0 = (CK == COEF_FIELD ? 3 : 0) + (HASN ? 1 : 0);
     if (A.p0 >= 0 && A.p0 != SP0) return cudaErrorNotSupported;
     if (P.base == BASE_IN && !P.p0) {
-        if (!P.out2) return launch_pair<T, CK, FCFL, SB_IN>(P, A, s, exact_eps);
-        if (!FCFL) return launch_pair<T, CK, false, SB_IN_OUT2>(P, A, s, exact_eps);
+        if (!P.out2) return launch_pair<T, CK, FCFL, SB_IN, HASN>(P, A, s, exact_eps);
+        if (!FCFL) return launch_pair<T, CK, false, SB_IN_OUT2, HASN>(P, A, s, exact_eps);
     }
-    if (P.base == BASE_RK3_S2 && P.p0 && !P.out2 && !FCFL) return launch_pair<T, CK, false, SB_S2>(P, A, s, exact_eps);
-    if (P.base == BASE_RK3_S3 && P.p0 && !P.out2) return launch_pair<T, CK, FCFL, SB_S3>(P, A, s, exact_eps);
-    if (P.base == BASE_P0 && P.p0 && !P.out2) return launch_pair<T, CK, FCFL, SB_P0>(P, A, s, exact_eps);
+    if (P.base == BASE_RK3_S2 && P.p0 && !P.out2 && !FCFL) return launch_pair<T, CK, false, SB_S2, HASN>(P, A, s, exact_eps);
+    if (P.base == BASE_RK3_S3 && P.p0 && !P.out2) return launch_pair<T, CK, FCFL, SB_S3, HASN>(P, A, s, exact_eps);
+    if (P.base == BASE_P0 && P.p0 && !P.out2) return launch_pair<T, CK, FCFL, SB_P0, HASN>(P, A, s, exact_eps);
     return cudaErrorNotSupported;
 }
 
@@ -503,9 +606,9 @@ cudaError_t launch_pair_sb(const StageParams<T>& P, const AuxList& A, cudaStream
 template <class T>
 cudaError_t launch_stage_pair3d(const StageParams<T>& P, const AuxList& A, cudaStream_t s, bool exact_eps) {
     if (pair_kernel_disabled() || tma_disabled() || !encode_tiled_fn()) return cudaErrorNotSupported;
-    if (P.nterms != 1) return cudaErrorNotSupported;
-    const TermDev& t0 = P.terms[0];
-    if (t0.kind != TERM_ADVECTION || t0.scheme != SCHEME_WENO5) return cudaErrorNotSupported;
+    if (P.nterms != 1 && P.nterms != 2) return cudaErrorNotSupported;
+    const TermDev& ta = P.terms[P.nterms - 1];          // the advection term (last)
+    if (ta.kind != TERM_ADVECTION || ta.scheme != SCHEME_WENO5) return cudaErrorNotSupported;
     const View<T>& v = P.in;
     if ((v.n[0] * sizeof(T)) % 16 != 0 || v.n[0] < 8 || v.n[1] < 8 || v.n[2] < 4) return cudaErrorNotSupported;
     if ((long)v.n[0] * v.n[1] >= (1L << 31)) return cudaErrorNotSupported;
@@ -515,9 +618,19 @@ cudaError_t launch_stage_pair3d(const StageParams<T>& P, const AuxList& A, cudaS
             const bool index_map = b.kind == BC_PERIODIC || b.kind == BC_SYMMETRY || (b.kind == BC_EXTRAP && b.P == 0) || (b.kind == BC_HALO && d == 2);
             if (!index_map) return cudaErrorNotSupported;
         }
-    if (t0.coef_kind == COEF_FIELD && A.first[0] == 0 && !t0.coef_f64)
+    if (P.nterms == 2) {
+        // (NormalMotionTerm(stored speed), AdvectionTerm(stored velocity)) in this order, Float64, no fused CFL
+        if constexpr (sizeof(T) == 8) {
+            const TermDev& tn = P.terms[0];
+            if (tn.kind != TERM_NORMAL || tn.coef_kind != COEF_FIELD || tn.coef_f64 != 0 || A.first[0] != 0) return cudaErrorNotSupported;
+            if (ta.coef_kind != COEF_FIELD || ta.coef_f64 != 0 || A.first[1] != 1 || P.cfl_out) return cudaErrorNotSupported;
+            return launch_pair_sb<T, COEF_FIELD, false, true>(P, A, s, exact_eps);
+        }
+        return cudaErrorNotSupported;
+    }
+    if (ta.coef_kind == COEF_FIELD && A.first[0] == 0 && !ta.coef_f64)
         return P.cfl_out ? launch_pair_sb<T, COEF_FIELD, true>(P, A, s, exact_eps) : launch_pair_sb<T, COEF_FIELD, false>(P, A, s, exact_eps);
-    if (t0.coef_kind == COEF_SEPARABLE)
+    if (ta.coef_kind == COEF_SEPARABLE)
         return P.cfl_out ? launch_pair_sb<T, COEF_SEPARABLE, true>(P, A, s, exact_eps) : launch_pair_sb<T, COEF_SEPARABLE, false>(P, A, s, exact_eps);
     return cudaErrorNotSupported;
 }

@@ -300,6 +300,41 @@ def test_pair_kernel_bitwise_vs_tiled(m, n):
             assert np.abs(outs[2][2].astype(np.float64) - outs[1][2].astype(np.float64)).max() <= tol
 
 
+@pytest.mark.parametrize("n", [(128, 64, 40), (72, 52, 37), (48, 48, 48)], ids=["128x64x40", "72x52x37", "48cube"])
+def test_pair_kernel_two_terms_vs_tiled(m, n):
+    """BASELINE config 5's term list (NormalMotionTerm(stored speed), AdvectionTerm(stored velocity)) through the x-pair kernel,
+    which shares the first / second differences between the ENO2 Godunov norm and WENO5 (the general tiled kernel forms
+    phi+ - 2 phi0 + phi- directly): same result up to rounding.  Speed with sign changes, every index-map BC, the three
+    integrators, anisotropic and isotropic meshes."""
+    ctx = m.default_context()
+    lc, hc = (0, 0, 0), (1, 1, 1)
+    x, y, z = H.coords(lc, hc, n)
+    phi = np.sqrt((x - 0.45) ** 2 + (y - 0.5) ** 2 + (z - 0.55) ** 2) - 0.25 + 0.03 * np.sin(7 * x) * np.cos(5 * y) * np.sin(6 * z)
+    v = H.bcast(0.2 * np.sin(4 * x + 1) * np.cos(3 * y) + 0.1 * z - 0.05, n)
+    sc, tabs = H.enright_tables(lc, hc, n)
+    tabs = [[t + 0.05 * (a + 1) for a, t in enumerate(row)] for row in tabs]
+    X, Y, Z = np.meshgrid(*[np.arange(k) for k in n], indexing="ij", sparse=True)
+    u = np.stack([((sc[d] * tabs[d][0][X]) * tabs[d][1][Y]) * tabs[d][2][Z] for d in range(3)], axis=0)
+    for k, bc in enumerate(PAIR_BCS):
+        case = H.Case("P5", lc, hc, n, phi, [dict(kind="normal", field=v), dict(kind="advection", field=u)], bc, np.float64)
+        integ = (m.RK3, m.RK2, m.ForwardEuler)[k % 3]
+        outs = []
+        for kernel in (4, 0, 3):
+            ctx.set_option(OPT_KERNEL, kernel)
+            ctx.reset_counters()
+            f = case.engine_field(m)
+            eq = m.LevelSetEquation(terms=case.engine_terms(m, f), ic=f, integrator=integ())
+            dt = 0.5 * m.compute_cfl(eq.terms, eq.state, 0.0)
+            m.integrate(eq, 4 * dt * (1 - 1e-12))
+            outs.append((eq.t, eq.steps_taken, eq.state.peek().copy(), ctx.counters()["pair_launches"]))
+        ctx.set_option(OPT_KERNEL, 0)
+        assert outs[0][3] > 0 and outs[1][3] > 0 and outs[2][3] == 0, "kernel selection"
+        assert outs[0][:2] == outs[1][:2] == outs[2][:2]
+        for o in outs[:2]:
+            d = np.abs(o[2] - outs[2][2]).max()
+            assert d <= 1e-12, (n, bc, integ.__name__, d)
+
+
 def _notched_sphere_case(n, dtype=np.float64):
     """3-D Zalesak-type body (sphere with a slot: kinks along the slot edges) in the Enright velocity: the sharp-feature
     counterpart of C3 for the x-pair kernel."""
