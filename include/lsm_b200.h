@@ -119,6 +119,17 @@ int32_t lsm_ctx_create(int32_t device, lsm_ctx** out);
  * torch.distributed, a file ...); then every rank creates its context. */
 int32_t lsm_nccl_unique_id(void* id128);
 int32_t lsm_ctx_create_rank(int32_t device, int32_t rank, int32_t nranks, const void* id128, lsm_ctx** out);
+/* Multi-GPU from ONE process (one Julia task / one Python thread driving a whole box): n_gpus contexts, rank r on
+ * device_ids[r], whose NCCL communicators come from ncclCommInitAll.  `out` receives n_gpus handles.  Per-rank calls without
+ * an exchange (lsm_field_create / upload / download / set_bc / fill / destroy) are made one context after the other; the
+ * collective ones (everything that exchanges halos or all-reduces: compute_cfl, stage, advance, integrate) must run on all
+ * ranks concurrently — the lsm_multi_* entry points below do that on one host thread per GPU and return the first error. */
+int32_t lsm_ctx_create_multi(int32_t n_gpus, const int32_t* device_ids, lsm_ctx** out);
+int32_t lsm_multi_compute_cfl(int32_t n_gpus, lsm_ctx* const* ctx, lsm_field* const* phi, const lsm_term* const* terms, int32_t nterms,
+                              double t, const double* gscale, double* dt_out);
+int32_t lsm_multi_integrate(int32_t n_gpus, lsm_ctx* const* ctx, int32_t integrator, double cfl, lsm_field* const* phi,
+                            const lsm_term* const* terms, int32_t nterms, double t0, double tf, double dt_max, int64_t max_steps,
+                            double* t_out, int64_t* steps_out);
 int32_t lsm_ctx_destroy(lsm_ctx* ctx);
 int32_t lsm_sync(lsm_ctx* ctx);
 int32_t lsm_set_option(lsm_ctx* ctx, int32_t option, int32_t value);

@@ -7,7 +7,7 @@ Julia API for this path), ``julia/`` (the ccall glue for the real package).
 """
 from . import _lib
 from ._lib import LSMError, CFLError, TimeError, BCError, build
-from .api import (Context, default_context, set_default_context, CartesianGrid, BoundaryCondition, PeriodicBC,
+from .api import (Context, MultiContext, integrate_multi, compute_cfl_multi, default_context, set_default_context, CartesianGrid, BoundaryCondition, PeriodicBC,
                   ExtrapolationBC, NeumannBC, LinearExtrapolationBC, SymmetryBC, MeshField, Upwind, WENO5,
                   TimeScaled, SeparableVelocity, LevelSetTerm, AdvectionTerm, CurvatureTerm, NormalMotionTerm,
                   EikonalReinitializationTerm, update_term, compute_cfl, TimeIntegrator, ForwardEuler, RK2, RK3,

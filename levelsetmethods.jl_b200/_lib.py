@@ -71,6 +71,10 @@ SYMBOLS = {
     "lsm_ctx_create": (_i32, [_i32, C.POINTER(_vp)]),
     "lsm_nccl_unique_id": (_i32, [_vp]),
     "lsm_ctx_create_rank": (_i32, [_i32, _i32, _i32, _vp, C.POINTER(_vp)]),
+    "lsm_ctx_create_multi": (_i32, [_i32, _pi32, C.POINTER(_vp)]),
+    "lsm_multi_compute_cfl": (_i32, [_i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.POINTER(lsm_term)), _i32, C.c_double, _pdbl, _pdbl]),
+    "lsm_multi_integrate": (_i32, [_i32, C.POINTER(_vp), _i32, C.c_double, C.POINTER(_vp), C.POINTER(C.POINTER(lsm_term)), _i32, C.c_double, C.c_double,
+                                   C.c_double, _i64, _pdbl, C.POINTER(_i64)]),
     "lsm_ctx_destroy": (_i32, [_vp]),
     "lsm_sync": (_i32, [_vp]),
     "lsm_set_option": (_i32, [_vp, _i32, _i32]),

@@ -39,6 +39,12 @@ class Context:
             buf = C.create_string_buffer(nccl_id, 128)
             L.check(L.lib().lsm_ctx_create_rank(device, rank, nranks, buf, C.byref(self.handle)))
 
+    @classmethod
+    def _wrap(cls, handle, device: int, rank: int, nranks: int) -> "Context":
+        c = cls.__new__(cls)
+        c.handle, c.rank, c.nranks, c.device = C.c_void_p(handle), rank, nranks, device
+        return c
+
     @staticmethod
     def nccl_unique_id() -> bytes:
         buf = C.create_string_buffer(128)
@@ -95,6 +101,61 @@ class Context:
 
 
 _default_ctx: Optional[Context] = None
+
+
+class MultiContext:
+    """All GPUs of a box driven from ONE process / thread (``lsm_ctx_create_multi``: ncclCommInitAll, one rank per device).
+    ``ranks[r]`` is an ordinary :class:`Context` (rank r of n): build the per-rank slabs with ``MeshField(global_array, grid,
+    ctx=mc.ranks[r])`` (or the device generators), then advance all of them together with :func:`integrate_multi`."""
+
+    def __init__(self, device_ids: Sequence[int]):
+        n = len(device_ids)
+        hs = (C.c_void_p * n)()
+        L.check(L.lib().lsm_ctx_create_multi(n, (C.c_int32 * n)(*device_ids), hs))
+        self.ranks = [Context._wrap(hs[r], int(device_ids[r]), r, n) for r in range(n)]
+
+    def __len__(self):
+        return len(self.ranks)
+
+    def close(self):
+        for c in self.ranks:
+            c.close()
+
+    @staticmethod
+    def gather(fields: Sequence["MeshField"]) -> np.ndarray:
+        """The global array from the per-rank slabs (concatenated along the decomposed, last axis)."""
+        return np.concatenate([np.asarray(f.peek()) for f in fields], axis=-1)
+
+
+def compute_cfl_multi(mc: MultiContext, terms_per_rank, phis, t: float) -> float:
+    n = len(mc)
+    lows = [_Lowered(terms_per_rank[r], phis[r], t) for r in range(n)]
+    dt = C.c_double()
+    L.check(L.lib().lsm_multi_compute_cfl(
+        n, (C.c_void_p * n)(*[c.handle for c in mc.ranks]), (C.c_void_p * n)(*[phis[r].device() for r in range(n)]),
+        (C.POINTER(L.lsm_term) * n)(*[C.cast(lw.arr, C.POINTER(L.lsm_term)) for lw in lows]), len(terms_per_rank[0]), float(t),
+        lows[0].gscale, C.byref(dt)))
+    return dt.value
+
+
+def integrate_multi(mc: MultiContext, eqs, tf: float, dt: float = inf):
+    """``integrate!`` of the same equation on every rank's slab, from one thread: ``eqs[r]`` is the rank's
+    :class:`LevelSetEquation` (device-only terms: stored / separable / constant coefficients, default hooks)."""
+    n = len(mc)
+    lows = [_Lowered(eqs[r].terms, eqs[r].state, eqs[r].t) for r in range(n)]
+    if not all(lw.device_only for lw in lows):
+        raise NotImplementedError("integrate_multi supports device-resident coefficients and default hooks")
+    t_out, st = C.c_double(), C.c_int64()
+    L.check(L.lib().lsm_multi_integrate(
+        n, (C.c_void_p * n)(*[c.handle for c in mc.ranks]), eqs[0].integrator.code, float(eqs[0].integrator.cfl),
+        (C.c_void_p * n)(*[eqs[r].state.device() for r in range(n)]),
+        (C.POINTER(L.lsm_term) * n)(*[C.cast(lw.arr, C.POINTER(L.lsm_term)) for lw in lows]), len(eqs[0].terms),
+        float(eqs[0].t), float(tf), float(dt), -1, C.byref(t_out), C.byref(st)))
+    for e in eqs:
+        e.state._mark_device_advanced()
+        e.t = t_out.value
+        e.steps_taken += st.value
+    return eqs
 
 
 def default_context() -> Context:

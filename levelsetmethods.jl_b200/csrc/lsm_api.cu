@@ -13,6 +13,7 @@
 #include <limits>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lsm_b200.h"
@@ -703,6 +704,23 @@ int32_t compute_cfl_impl(lsm_ctx* ctx, lsm_field* phi, const lsm_term* terms, in
 }  // namespace
 
 // =================================================================================================
+namespace {
+// run f(r) for every rank on its own host thread (NCCL collectives of the ranks must be in flight together); the first failing
+// rank's status and message are handed back to the calling thread
+template <class F>
+int32_t fan_out(int n, F f) {
+    std::vector<int32_t> rcs(n, LSM_OK);
+    std::vector<std::string> msgs(n);
+    std::vector<std::thread> th;
+    th.reserve(n);
+    for (int r = 0; r < n; ++r) th.emplace_back([&, r] { rcs[r] = f(r); if (rcs[r] != LSM_OK) msgs[r] = g_err; });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < n; ++r) if (rcs[r] != LSM_OK) { g_err = msgs[r]; return rcs[r]; }
+    return LSM_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int32_t lsm_abi_version(void) { return LSM_ABI_VERSION; }
@@ -756,6 +774,56 @@ int32_t lsm_ctx_create_rank(int32_t device, int32_t rank, int32_t nranks, const 
     ncclResult_t r = nccl().CommInitRank(&c->nccl_comm, nranks, id, rank);
     if (r != ncclSuccess) { c->nccl_comm = nullptr; lsm_ctx_destroy(c); return fail(LSM_ERR_NCCL, "ncclCommInitRank failed: %s", nccl().GetErrorString(r)); }
     *out = c;
+    return LSM_OK;
+}
+
+int32_t lsm_ctx_create_multi(int32_t n, const int32_t* devs, lsm_ctx** out) {
+    if (!devs || !out || n < 1 || n > 64) return fail(LSM_ERR_ARG, "bad argument");
+    if (n == 1) return lsm_ctx_create(devs[0], out);
+    const char* why = "";
+    if (!nccl().load(&why)) return fail(LSM_ERR_NCCL, "cannot load NCCL: %s", why);
+    for (int r = 0; r < n; ++r) out[r] = nullptr;
+    int32_t rc = LSM_OK;
+    for (int r = 0; r < n && rc == LSM_OK; ++r) {
+        lsm_ctx* c = new (std::nothrow) lsm_ctx();
+        if (!c) { rc = fail(LSM_ERR_OOM, "host allocation failed"); break; }
+        c->device = devs[r]; c->rank = r; c->nranks = n;
+        out[r] = c;
+        rc = ctx_common_init(c);
+    }
+    if (rc == LSM_OK) {
+        std::vector<ncclComm_t> comms(n);
+        std::vector<int> ids(devs, devs + n);
+        ncclResult_t r = nccl().CommInitAll(comms.data(), n, ids.data());
+        if (r != ncclSuccess) rc = fail(LSM_ERR_NCCL, "ncclCommInitAll failed: %s", nccl().GetErrorString(r));
+        else for (int k = 0; k < n; ++k) out[k]->nccl_comm = comms[k];
+    }
+    if (rc != LSM_OK) {
+        const std::string msg = g_err;
+        for (int r = 0; r < n; ++r) if (out[r]) { lsm_ctx_destroy(out[r]); out[r] = nullptr; }
+        g_err = msg;
+    }
+    return rc;
+}
+
+int32_t lsm_multi_compute_cfl(int32_t n, lsm_ctx* const* ctx, lsm_field* const* phi, const lsm_term* const* terms, int32_t nterms,
+                              double t, const double* gscale, double* dt_out) {
+    if (!ctx || !phi || !terms || !dt_out || n < 1) return fail(LSM_ERR_ARG, "bad argument");
+    std::vector<double> dts(n, 0.0);
+    TRY(fan_out(n, [&](int r) { return lsm_compute_cfl(ctx[r], phi[r], terms[r], nterms, t, gscale, &dts[r]); }));
+    *dt_out = dts[0];        // all-reduced: identical on every rank
+    return LSM_OK;
+}
+
+int32_t lsm_multi_integrate(int32_t n, lsm_ctx* const* ctx, int32_t integrator, double cfl, lsm_field* const* phi,
+                            const lsm_term* const* terms, int32_t nterms, double t0, double tf, double dt_max, int64_t max_steps,
+                            double* t_out, int64_t* steps_out) {
+    if (!ctx || !phi || !terms || n < 1) return fail(LSM_ERR_ARG, "bad argument");
+    std::vector<double> ts(n, t0);
+    std::vector<int64_t> st(n, 0);
+    TRY(fan_out(n, [&](int r) { return lsm_integrate(ctx[r], integrator, cfl, phi[r], terms[r], nterms, t0, tf, dt_max, max_steps, &ts[r], &st[r]); }));
+    if (t_out) *t_out = ts[0];
+    if (steps_out) *steps_out = st[0];
     return LSM_OK;
 }
 

@@ -11,6 +11,7 @@ struct NcclApi {
     void* handle = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -31,6 +32,7 @@ struct NcclApi {
         if (!field) { *why = "missing NCCL symbol " sym; dlclose(handle); handle = nullptr; return false; }
         LSM_SYM(GetUniqueId, "ncclGetUniqueId")
         LSM_SYM(CommInitRank, "ncclCommInitRank")
+        LSM_SYM(CommInitAll, "ncclCommInitAll")
         LSM_SYM(CommDestroy, "ncclCommDestroy")
         LSM_SYM(Send, "ncclSend")
         LSM_SYM(Recv, "ncclRecv")
