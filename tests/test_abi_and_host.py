@@ -156,3 +156,24 @@ def test_fails_loudly_without_the_extension(tmp_path):
     env = dict(os.environ, LSM_B200_SO=str(tmp_path / "does_not_exist.so"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
     assert "LOUD True" in out.stdout, out.stdout + out.stderr
+
+
+def test_julia_glue_binds_declared_entry_points_with_matching_arity():
+    """julia/LSMB200.jl cannot run here (no Julia in the image): at least every `ccall((:name, LIB), ret, (argtypes...), ...)`
+    must name a function include/lsm_b200.h declares, with as many argument types as the C prototype has parameters, and the
+    module must define methods on the reference's seam functions (timestepping.jl:101,126-202; levelsetterms.jl:22)."""
+    hdr = open(os.path.join(ROOT, "include", "lsm_b200.h")).read()
+    src = open(os.path.join(ROOT, "levelsetmethods.jl_b200", "julia", "LSMB200.jl")).read()
+    protos = {}
+    for mm in re.finditer(r"\b(?:int32_t|const char\*)\s+(lsm_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, re.S):
+        args = mm.group(2).strip()
+        protos[mm.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    calls = re.findall(r"ccall\(\(:(lsm_[a-z0-9_]+), LIB\),\s*\w+,\s*\(([^()]*)\)", src, re.S)
+    assert len(calls) >= 18
+    for name, argt in calls:
+        assert name in protos, f"{name} is not declared in the header"
+        n = 0 if argt.strip() == "" else len([a for a in re.split(r",(?![^{]*})", argt) if a.strip()])
+        assert n == protos[name], f"{name}: Julia passes {n} argument types, the C prototype has {protos[name]}"
+    for seam in ("LSM._integrate!(ls, ϕ::DeviceMeshField", "LSM._alloc_buffers(", "LSM._advance!(", "LSM.compute_cfl(terms, ϕ::DeviceMeshField",
+                 "<: LSM.AbstractMeshField{N, T, V}", "LSM.update_band!(ϕ::DeviceMeshField"):
+        assert seam in src, seam
