@@ -80,6 +80,7 @@ struct lsm_ctx {
     std::vector<CflCacheEntry> cfl_cache;
     std::vector<CflCand> cfl_cand;
     int opt_cand = 1;           // LSM_OPT_CFL_CANDIDATES
+    int stage_skip_zero_u = 0;  // transient: set by lsm_extend_along_normals around its stages (StageParams::skip_zero_u)
     unsigned* d_cand_count = nullptr; double* d_cand = nullptr; double* h_cand = nullptr;   // candidate staging (device / pinned)
     void* stage[2] = {nullptr, nullptr};        // AoS <-> SoA staging chunks of vector-field transfers (allocated on first use)
     cudaEvent_t ev_stage[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
@@ -367,6 +368,7 @@ int32_t run_stage_t(lsm_ctx* c, lsm_field* in, lsm_field* p0, lsm_field* out, ls
     P.dxmin = dxmin;
     for (int k = 0; k < nterms; ++k) TRY(make_term_dev(in, terms[k], term_scale(terms[k], tstage, gscale, k), &P.terms[k]));
     P.cfl_out = nullptr; P.cfl_g = 0; P.cfl_tau = 0;
+    P.skip_zero_u = c->stage_skip_zero_u;
     if (c->fuse_req.on) {
         c->fuse_req.on = false;
         const TermDev& t0 = P.terms[0];
@@ -1360,7 +1362,11 @@ int32_t lsm_extend_along_normals(lsm_ctx* ctx, lsm_field* F, lsm_field* phi, int
         const double tau = cfl * dx;
         lsm_term term{};
         term.kind = LSM_TERM_ADVECTION; term.scheme = LSM_UPWIND; term.coef_kind = LSM_COEF_FIELD; term.tscale_kind = LSM_TS_NONE; term.field = vel;
+        // frozen / degenerate nodes carry a zero velocity: with skip_zero_u they keep their value exactly even when a neighbour of
+        // F is NaN / Inf (F is often undefined away from the interface) — the reference copies them untouched (velocityextension.jl:53-56)
+        ctx->stage_skip_zero_u = 1;
         for (int it = 0; it < nb_iters && rc == LSM_OK; ++it) rc = stage_impl(ctx, LSM_FORWARD_EULER, 1, F, &term, 1, 0.0, tau, nullptr);
+        ctx->stage_skip_zero_u = 0;
     }
     cudaStreamSynchronize(ctx->comm);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);

@@ -188,7 +188,7 @@ __device__ inline double godunov_norm(const Reader<N, T>& r, const double* h, bo
 }
 
 template <int N, class T>
-__device__ inline double compute_term(const Reader<N, T>& r, const TermDev& t, long node, const double* h, double dxmin) {
+__device__ inline double compute_term(const Reader<N, T>& r, const TermDev& t, long node, const double* h, double dxmin, int skip_zero_u = 0) {
     switch (t.kind) {
         case TERM_ADVECTION: {   // levelsetterms.jl:73-82
             double s = 0.0;
@@ -201,6 +201,7 @@ __device__ inline double compute_term(const Reader<N, T>& r, const TermDev& t, l
                     else       der = weno5_strict(Dp(r, d, 2, h[d]), Dp(r, d, 1, h[d]), Dp(r, d, 0, h[d]), Dp(r, d, -1, h[d]), Dp(r, d, -2, h[d]));
                 } else {
                     der = (v > 0) ? Dm(r, d, 0, h[d]) : Dp(r, d, 0, h[d]);
+                    if (skip_zero_u && v == 0.0) der = 0.0;
                 }
                 const double p = v * der;
                 s = (d == 0) ? p : s + p;
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(const __grid_constan
     }
     T x2 = inc;
     for (int k = 0; k < P.nterms; ++k) {
-        const double H = compute_term<N, T>(r, P.terms[k], node, P.h, P.dxmin);
+        const double H = compute_term<N, T>(r, P.terms[k], node, P.h, P.dxmin, P.skip_zero_u);
         x = T(double(x) - P.c * H);
         if (P.out2) x2 = T(double(x2) - P.c2 * H);
     }

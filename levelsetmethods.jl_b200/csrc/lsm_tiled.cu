@@ -365,7 +365,8 @@ stage_tiled_kernel(const __grid_constant__ StageParams<T> P, const __grid_consta
 #pragma unroll
                         for (int d = 0; d < NDIM; ++d) {
                             const double u = coef(tm, kk, d, kc);
-                            const double der = u > 0 ? double(T(qc - at(d, -1))) : double(T(at(d, 1) - qc));
+                            double der = u > 0 ? double(T(qc - at(d, -1))) : double(T(at(d, 1) - qc));
+                            if (P.skip_zero_u && u == 0.0) der = 0.0;
                             const double a = u * ih[d];
                             H = d == 0 ? a * der : fma(a, der, H);
                         }

@@ -727,6 +727,21 @@ def test_extend_along_normals(m, O, strict, dtype):
                         assert np.array_equal(F.peek()[mask], F0[mask])          # Dirichlet constraint on frozen nodes
     with pytest.raises(ValueError):
         m.extend_along_normals(F, phi, nb_iters=-1)
+    # F undefined (NaN) away from the interface: frozen nodes keep their values exactly (velocityextension.jl:53-56 copies them),
+    # even where a neighbour is NaN — 0 * NaN must not leak into them
+    n, lc, hc = (64, 56), (-1, -1), (1, 1)
+    X = H.coords(lc, hc, n)
+    phi0 = H.bcast(np.sqrt(X[0] ** 2 + X[1] ** 2) - 0.5, n).astype(dtype)
+    mask = np.asfortranarray(np.abs(phi0) < 0.06)
+    near = np.asfortranarray(np.abs(phi0) < 0.075)
+    F0 = np.where(near, H.bcast(np.sin(3 * X[0]) + X[1] ** 2, n), np.nan).astype(dtype)
+    for kernel in (1, 0):
+        ctx.set_option(OPT_KERNEL, kernel)
+        g = m.CartesianGrid(lc, hc, n)
+        F = m.MeshField(F0.copy(order="F"), g)
+        m.extend_along_normals(F, m.MeshField(phi0.copy(order="F"), g, bc=m.NeumannBC()), nb_iters=3, frozen=mask)
+        assert np.array_equal(F.peek()[mask], F0[mask]) and not np.isnan(F.peek()[mask]).any()
+    ctx.set_option(OPT_KERNEL, 0)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
