@@ -119,7 +119,7 @@ def build(force: bool = False) -> str:
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "lsm_b200.h"))
     stale = (not os.path.exists(SO_PATH)) or os.path.getmtime(SO_PATH) < max(os.path.getmtime(s) for s in srcs)
     if force or stale:
-        subprocess.run(["make", "-C", CSRC, "-s", "-j4"] + (["-B"] if force else []), check=True)
+        subprocess.run(["make", "-C", CSRC, "-s", f"-j{min(8, os.cpu_count() or 4)}"] + (["-B"] if force else []), check=True)
     return SO_PATH
 
 

@@ -635,7 +635,12 @@ cudaError_t launch_stage_pair3d(const StageParams<T>& P, const AuxList& A, cudaS
     return cudaErrorNotSupported;
 }
 
+// The Makefile compiles this file twice (-DLSM_PAIR_F32 / -DLSM_PAIR_F64) so that the two halves build in parallel.
+#if !defined(LSM_PAIR_F64)
 template cudaError_t launch_stage_pair3d<float>(const StageParams<float>&, const AuxList&, cudaStream_t, bool);
+#endif
+#if !defined(LSM_PAIR_F32)
 template cudaError_t launch_stage_pair3d<double>(const StageParams<double>&, const AuxList&, cudaStream_t, bool);
+#endif
 
 }  // namespace lsm
