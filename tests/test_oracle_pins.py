@@ -224,6 +224,19 @@ def test_timestepping_orders(O):
 
 
 # ---- test/test-levelsetequation.jl:26-65 ----
+def test_weno5_exact_rational_vectors(O):
+    """`_weno5` against the reference formula evaluated in exact rational arithmetic (tests/golden/make_weno5_vectors.py;
+    dyadic inputs, exact values of the Float64 literals): independent of any rounding order, so it pins coefficients, signs
+    and the structure of the weights to a few ulp."""
+    import json
+    L = O.lib()
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_known_answers.json")))["weno5_exact"]
+    assert len(g["cases"]) >= 7
+    for c in g["cases"]:
+        got = L.orc_weno5(*c["v"])
+        assert got == pytest.approx(c["expected"], rel=g["rel_tol"], abs=0.0), (c, got)
+
+
 def test_weno5_and_upwind_spatial_order(O):
     Ns = [20, 40, 80]
     e = [_adv_err_1d(O, O.RK3, N, cfl=1e-2) for N in Ns]
