@@ -1,20 +1,21 @@
 #!/bin/bash
 # Round profile pass on a B200 box (run through gpurun from the repo root):
-#   bash tools/profile_round.sh            -> everything lands in gpurun_out/, summaries are copied to profiles/ by hand
+#   bash tools/profile_round.sh [nofull]     -> everything lands in gpurun_out/, summaries are copied to profiles/ by hand
 # Every ncu command runs only after the same command exited 0 without ncu; numbers printed under ncu are never bench values.
 set -x
 O=gpurun_out
-python bench.py > $O/bench_c3_1gpu.json 2> $O/bench_c3_1gpu.err || exit 1
-python tools/bench_configs.py > $O/configs.jsonl 2> $O/configs.err || exit 1
+R=${ROUND:-r02}
+timeout 600 python bench.py > $O/bench_c3_1gpu_$R.json 2> $O/bench_c3_1gpu_$R.err || exit 1
+timeout 900 python tools/bench_configs.py > $O/configs_$R.jsonl 2> $O/configs_$R.err || exit 1
 B="python bench.py --n 512 --steps 2 --warmup 3 --no-cpu --no-e2e"
-$B > $O/plain.log 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 30 --csv \
-    --log-file $O/launches.csv $B > $O/ncu_launches.log 2>&1
+timeout 300 $B > $O/plain.log 2>&1 || exit 1
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 40 --csv \
+    --log-file $O/launches_$R.csv $B > $O/ncu_launches.log 2>&1
 if [ "$1" != "nofull" ]; then
-ncu --set full --clock-control none --import-source on -k regex:stage_tiled -s 10 -c 3 -f -o $O/prof_c3 $B > $O/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:pair3d -s 6 -c 3 -f -o $O/prof_c3_$R $B > $O/ncu_full.log 2>&1
 fi
 # one RK step of every BASELINE configuration under ncu (sections, not --set full): every specialised kernel once
 K="python tools/bench_configs.py --steps 1 --warmup 0 --reps 1 --skip C1"
-$K > $O/cfg1.log 2>&1 && ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section ComputeWorkloadAnalysis --section SchedulerStats \
-    --section WarpStateStats --section LaunchStats --section Occupancy --clock-control none -k regex:stage_tiled -c 30 --csv --page raw \
-    --log-file $O/ncu_kernels.csv $K > $O/ncu_kernels.log 2>&1
+timeout 600 $K > $O/cfg1.log 2>&1 && timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section ComputeWorkloadAnalysis --section SchedulerStats \
+    --section WarpStateStats --section LaunchStats --section Occupancy --clock-control none -k "regex:stage_tiled|pair3d" -c 30 --csv --page raw \
+    --log-file $O/ncu_kernels_$R.csv $K > $O/ncu_kernels.log 2>&1
