@@ -139,6 +139,7 @@ int32_t ctx_common_init(lsm_ctx* c) {
     CU(cudaMalloc(&c->d_scalar, 64));
     CU(cudaMallocHost(&c->h_scalar, 64));
     if (getenv("LSM_B200_NO_FUSE_CFL")) c->opt_fuse_cfl = 0;
+    if (getenv("LSM_B200_NO_OVERLAP")) c->opt_overlap = 0;
     if (getenv("LSM_B200_NO_GRAPH")) c->opt_graph = 0;
     return LSM_OK;
 }

@@ -19,6 +19,7 @@
 // The arithmetic is the SAME sequence of operations as lsm_tiled.cu's weno5_up / stage combination, so the two
 // kernels agree bit for bit (tests/test_gpu_parity.py::test_pair_kernel_bitwise_vs_tiled) and both stay within
 // 1e-10 of the oracle after 100 RK3 steps.
+#include <algorithm>
 #include "lsm_tile_util.cuh"
 
 namespace lsm {
@@ -568,8 +569,15 @@ cudaError_t launch_pair_x(const StageParams<T>& P, const AuxList& A, cudaStream_
     if ((uintptr_t)base % 16 != 0 || !cached_map3<T>(&M.phi, base, v.n[0], v.n[1], (long)v.n[2] + 2L * v.halo, G::W, G::HH)) return cudaErrorNotSupported;
     for (int a = 0; a < NAUX; ++a)
         if ((uintptr_t)A.src[a] % 16 != 0 || !cached_map3<T>(&M.aux[a], A.src[a], v.n[0], v.n[1], v.n[2], G::BX, G::BY)) return cudaErrorNotSupported;
+    // z chunk per block: ~64 planes (the 7-plane prologue of a chunk is then < 3 % of its time and hides behind the SM's other block),
+    // split evenly (120 planes of a 1024^3 / 8-GPU slab -> 2 x 60, not 32 + 32 + 32 + 24), but short enough that the grid still fills
+    // the 148 x 2 block slots about twice
     const int nr = P.r1 - P.r0;
-    const int cz = nr >= 128 ? 64 : (nr >= 32 ? 32 : nr);
+    const long tiles = (long)((v.n[0] + G::BX - 1) / G::BX) * ((v.n[1] + G::BY - 1) / G::BY);
+    int nchunks = std::max(1, (nr + 32) / 64);
+    const long want = (2L * 296 + tiles - 1) / tiles;                  // chunks needed for ~2 waves
+    if (nchunks < want) nchunks = (int)std::min<long>(want, std::max(1, nr / 8));
+    const int cz = (nr + nchunks - 1) / nchunks;
     dim3 block(32, NT / 32), grid((v.n[0] + G::BX - 1) / G::BX, (v.n[1] + G::BY - 1) / G::BY, (nr + cz - 1) / cz);
     kern<<<grid, block, smem, s>>>(P, A, M, cz);
     return cudaGetLastError();
