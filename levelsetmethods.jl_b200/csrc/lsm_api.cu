@@ -345,7 +345,7 @@ int32_t launch_stage_range(lsm_ctx* c, int ndim, StageParams<T>& P, int r0, int 
     P.r0 = r0; P.r1 = r1;
     cudaError_t e = cudaErrorNotSupported;
     int used_pair = 0;
-    if (c->opt_kernel != 1 && stage_tiled_supported<T>(ndim, P)) e = launch_stage_tiled<T>(ndim, P, c->sm_count, st, c->opt_kernel == 3 ? 0 : (c->opt_kernel == 4 ? 2 : 1), &used_pair);
+    if (c->opt_kernel != 1 && stage_tiled_supported<T>(ndim, P)) e = launch_stage_tiled<T>(ndim, P, c->sm_count, st, c->opt_kernel == 3 ? 0 : (c->opt_kernel == 4 ? 2 : (c->opt_kernel == 2 ? 3 : 1)), &used_pair);
     else if (c->opt_kernel == 2) return fail(LSM_ERR_UNSUPPORTED, "tiled kernel forced but this configuration is not covered");
     if (e == cudaErrorNotSupported) e = launch_stage_generic<T>(ndim, P, st);
     if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "stage kernel launch failed: %s", cudaGetErrorString(e));

@@ -62,10 +62,12 @@ struct AuxList {
 
 // lsm_pair3d.cu (3-D single-term WENO5 advection, x-pair threads).  cudaErrorNotSupported -> use the general tiled kernel.
 template <class T> cudaError_t launch_stage_pair3d(const StageParams<T>& P, const AuxList& A, cudaStream_t s, bool exact_eps);
+// lsm_pair2d.cu (2-D WENO5 advection [+ constant-b curvature], x-pair threads marching along y)
+template <class T> cudaError_t launch_stage_pair2d(const StageParams<T>& P, const AuxList& A, cudaStream_t s, bool force, int sm_count);
 
 // lsm_tiled.cu (performance kernels).  Returns cudaErrorNotSupported when the configuration is
 // not covered, in which case the caller uses the generic kernel.
-template <class T> cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, cudaStream_t s, int pair_mode = 1, int* used_pair = nullptr);   // pair_mode: 0 never, 1 x-pair kernel (20-bit eps max), 2 x-pair kernel with the exact eps max
+template <class T> cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, cudaStream_t s, int pair_mode = 1, int* used_pair = nullptr);   // pair_mode: 0 never, 1 x-pair kernels (3-D: 20-bit eps max), 2 3-D x-pair kernel with the exact eps max, 3 x-pair kernels forced on small 2-D grids too
 template <class T> bool stage_tiled_supported(int ndim, const StageParams<T>& P);
 
 }  // namespace lsm

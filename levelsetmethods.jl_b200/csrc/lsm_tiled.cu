@@ -627,6 +627,10 @@ cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, 
         const cudaError_t e = launch_stage_pair3d<T>(P, A, s, pair_mode == 2);
         if (e != cudaErrorNotSupported) { if (used_pair) *used_pair = 1; return e; }
     }
+    if (pair_mode && ndim == 2 && (mask == M_ADV_WENO || (mask == (M_ADV_WENO | M_CURV) && P.nterms == 2))) {      // 2-D x-pair kernel (lsm_pair2d.cu)
+        const cudaError_t e = launch_stage_pair2d<T>(P, A, s, pair_mode == 3, sm_count);
+        if (e != cudaErrorNotSupported) { if (used_pair) *used_pair = 1; return e; }
+    }
     bool remap = true;     // every BC an index map?  (ExtrapolationBC{P>=1} is a weighted stencil)
     for (int d = 0; d < ndim; ++d)
         for (int sd = 0; sd < 2; ++sd)

@@ -335,6 +335,45 @@ def test_pair_kernel_two_terms_vs_tiled(m, n):
             assert d <= 1e-12, (n, bc, integ.__name__, d)
 
 
+@pytest.mark.parametrize("n", [(256, 96), (520, 70), (40, 33), (1032, 24)], ids=["256x96", "520x70", "40x33", "1032x24"])
+def test_pair2d_kernel_vs_tiled(m, n):
+    """The 2-D x-pair kernel (csrc/lsm_pair2d.cu: strips marching along y on a TMA row ring, lazy x-ghost fix-up two rows ahead
+    for the curvature corners) against the general tiled 2-D kernel (LSM_OPT_KERNEL = 3): advection alone (C1's term list) and
+    advection + constant-b curvature (C2's), every index-map BC, FE / RK2 / RK3, both dtypes, partial strips, sign changes of
+    the velocity.  Same operations, so the states must agree to rounding level (bit-identical in practice)."""
+    ctx = m.default_context()
+    lc, hc = (-1.0, -1.0), (1.0, 1.0)
+    x, y = H.coords(lc, hc, n)
+    phi = np.hypot(x - 0.1, y + 0.05) - 0.45 + 0.03 * np.sin(9 * x) * np.cos(7 * y)
+    phi = np.maximum(phi, -(np.maximum(np.abs(x - 0.1) - 0.08, np.abs(y + 0.4) - 0.3)))        # a notch: kinks for the curvature term
+    u = np.stack([H.bcast(-y + 0.2 * np.sin(5 * x), n), H.bcast(x + 0.1 * np.cos(4 * y), n)], axis=0)
+    bcs = [("neumann",), ("periodic",), ("symmetry",), ((("neumann",), ("symmetry",)), ("periodic",))]
+    k = 0
+    for bc in bcs:
+        for dtype in (np.float64, np.float32):
+            if dtype == np.float32 and n[0] % 4:
+                continue
+            for curv in (False, True):
+                k += 1
+                terms = [dict(kind="advection", field=u)] + ([dict(kind="curvature", const=-0.01)] if curv else [])
+                case = H.Case("P2", lc, hc, n, phi, terms, bc, dtype)
+                integ = (m.RK3, m.RK2, m.ForwardEuler)[k % 3]
+                outs = []
+                for kernel in (2, 3):                      # 2: x-pair kernel forced (also below its size threshold), 3: tiled only
+                    ctx.set_option(OPT_KERNEL, kernel)
+                    ctx.reset_counters()
+                    f = case.engine_field(m)
+                    eq = m.LevelSetEquation(terms=case.engine_terms(m, f), ic=f, integrator=integ())
+                    dt = 0.5 * m.compute_cfl(eq.terms, eq.state, 0.0)
+                    m.integrate(eq, 4 * dt * (1 - 1e-12))
+                    outs.append((eq.t, eq.steps_taken, eq.state.peek().copy(), ctx.counters()["pair_launches"]))
+                ctx.set_option(OPT_KERNEL, 0)
+                assert outs[0][3] > 0 and outs[1][3] == 0, "kernel selection"
+                assert outs[0][:2] == outs[1][:2]
+                d = np.abs(outs[0][2].astype(np.float64) - outs[1][2].astype(np.float64)).max()
+                assert d <= (1e-13 if dtype == np.float64 else 1e-6), (n, bc, np.dtype(dtype).name, curv, integ.__name__, d)
+
+
 def _notched_sphere_case(n, dtype=np.float64):
     """3-D Zalesak-type body (sphere with a slot: kinks along the slot edges) in the Enright velocity: the sharp-feature
     counterpart of C3 for the x-pair kernel."""
