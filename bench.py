@@ -37,7 +37,8 @@ METRIC = "cell-updates/s per RK3 step (3D WENO5 advection, Float64)"
 UNIT = "cell-updates/s"
 PERIOD = 3.0
 B_ALG = 136.0          # bytes per cell-update, 3-D f64 RK3 advection with a stored velocity: (8 + 3N) * s
-CPU_SAMPLE_N = 128     # the CPU legs run the same configuration on a 128^3 grid (bounded sample: ~0.2 s per RK3 step on 16 cores)
+CPU_SAMPLE_N = 128     # cpu_baseline leg of the main line: the same configuration on a 128^3 grid (~0.12 s per RK3 step on 16 cores)
+REF_SAMPLE_N = 256     # --impl reference: a 256^3 grid (~1 s per RK3 step on 16 cores; 512^3 would take ~8 s per step)
 
 
 def enright_tables(n, nz_glob, lz):
@@ -131,14 +132,14 @@ def ncu_traffic():
         return None
 
 
-def cpu_leg(steps, warmup, threads):
-    """The CPU oracle on a CPU_SAMPLE_N^3 grid of the same configuration; returns (updates/s, seconds/step)."""
+def cpu_leg(steps, warmup, threads, n=CPU_SAMPLE_N):
+    """The CPU oracle on an n^3 grid of the same configuration; returns (updates/s, seconds/step)."""
     import oracle as O
     import helpers as H
     O.set_threads(threads)
-    case = H.c3_enright(CPU_SAMPLE_N, period=PERIOD)
+    case = H.c3_enright(n, period=PERIOD)
     f, terms = case.oracle_field(), case.oracle_terms()
-    nodes = CPU_SAMPLE_N ** 3
+    nodes = n ** 3
     t = 0.0
     for _ in range(warmup):
         dt = 0.5 * O.compute_cfl(f, terms, t)
@@ -166,14 +167,14 @@ def run_reference(args, rank):
     if rank != 0:
         return
     threads = host_threads()
-    v, sps = cpu_leg(args.steps, max(args.warmup, 1), threads)
+    v, sps = cpu_leg(args.steps, max(args.warmup, 1), threads, REF_SAMPLE_N)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C3 Enright sphere, {CPU_SAMPLE_N}^3 sample of the 512^3 config, WENO5+RK3, NeumannBC, stored velocity x cos(pi t/3)"},
+        "config": {"workload": f"C3 Enright sphere, {REF_SAMPLE_N}^3 sample of the 512^3 config, WENO5+RK3, NeumannBC, stored velocity x cos(pi t/3)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{CPU_SAMPLE_N}^3 grid, {args.steps} RK3 steps, OpenMP over the slowest axis; C++ restatement of the "
+                         "sample": f"{REF_SAMPLE_N}^3 grid, {args.steps} RK3 steps, OpenMP over the slowest axis; C++ restatement of the "
                                    "reference (oracle/), not Julia — the reference's hot loop itself is serial"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
