@@ -73,12 +73,58 @@ __device__ __forceinline__ double weno_core(const WenoK&, float d0, float d1, fl
     return double(fmaf(num, __frcp_rn(den), d2));
 }
 
+// The Float32 evaluation for TWO nodes at once with Blackwell's packed FP32 instructions (FFMA2 / FADD2 / FMUL2: one issue slot
+// for both nodes; .x = node A, .y = node B).  Lane-wise IEEE, same operation order as the scalar version above, so the results
+// are bit-identical to it; max|d| and the two reciprocals stay scalar (no packed FMNMX / MUFU).
+#ifndef LSM_NO_F32X2
+__device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
+__device__ __forceinline__ float2 f2(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ void weno_core2(float2 d0, float2 d1, float2 d2, float2 d3, float2 d4, double& WA, double& WB) {
+    const float2 e1 = sub2(d1, d0), e2 = sub2(d2, d1), e3 = sub2(d3, d2), e4 = sub2(d4, d3);
+    const float ma = fmaxf(fmaxf(fmaxf(fabsf(d0.x), fabsf(d1.x)), fmaxf(fabsf(d2.x), fabsf(d3.x))), fabsf(d4.x));
+    const float mb = fmaxf(fmaxf(fmaxf(fabsf(d0.y), fabsf(d1.y)), fmaxf(fabsf(d2.y), fabsf(d3.y))), fabsf(d4.y));
+    const float2 im = f2(ma > 0.f ? __frcp_rn(ma) : 0.f, mb > 0.f ? __frcp_rn(mb) : 0.f);
+    const float2 s1 = __fmul2_rn(e1, im), s2 = __fmul2_rn(e2, im), s3 = __fmul2_rn(e3, im), s4 = __fmul2_rn(e4, im);
+    const float2 c133 = f2(13.0f / 3.0f), epsf = f2(4.0e-6f);
+    const float2 t1a = sub2(s2, s1), t1b = sub2(s3, s2), t1c = sub2(s4, s3);
+    const float2 t2a = __ffma2_rn(f2(3.0f), s2, f2(-s1.x, -s1.y)), t2b = __fadd2_rn(s2, s3), t2c = __ffma2_rn(f2(-3.0f), s3, s4);
+    const float2 b1 = __ffma2_rn(t2a, t2a, __ffma2_rn(c133, __fmul2_rn(t1a, t1a), epsf));
+    const float2 b2 = __ffma2_rn(t2b, t2b, __ffma2_rn(c133, __fmul2_rn(t1b, t1b), epsf));
+    const float2 b3 = __ffma2_rn(t2c, t2c, __ffma2_rn(c133, __fmul2_rn(t1c, t1c), epsf));
+    const float2 p12 = __fmul2_rn(b1, b2), p13 = __fmul2_rn(b1, b3), p23 = __fmul2_rn(b2, b3);
+    const float2 w1 = __fmul2_rn(p23, p23), w2 = __fmul2_rn(p13, p13), w3 = __fmul2_rn(p12, p12);
+    const float2 den = __ffma2_rn(f2(3.0f), w3, __ffma2_rn(f2(6.0f), w2, w1));
+    const float2 G1 = __ffma2_rn(f2(5.0f / 6.0f), e2, __fmul2_rn(f2(-1.0f / 3.0f), e1));
+    const float2 G2 = __ffma2_rn(f2(2.0f), e3, e2);
+    const float2 G3 = __ffma2_rn(f2(2.0f), e3, __fmul2_rn(f2(-0.5f), e4));
+    const float2 num = __ffma2_rn(w3, G3, __ffma2_rn(w2, G2, __fmul2_rn(w1, G1)));
+    const float2 r = __ffma2_rn(num, f2(__frcp_rn(den.x), __frcp_rn(den.y)), d2);
+    WA = double(r.x); WB = double(r.y);
+}
+#endif
+
 // h * (the upwind-biased WENO5 derivative) at two nodes A and B along one dimension.  a[k] / b[k] is phi at offset k - 3 from
 // node A / B; xa / xb carries sign(u * g) of the node in bit 31 (set: plus-biased stencil, derivatives.jl:109-121; clear:
 // minus-biased, :89-101).  When B is A's neighbour along the dimension the caller passes b[k] = a[k + 1] and the common
 // differences are shared by the compiler's value numbering.
 template <class T, bool XMAX>
 __device__ __forceinline__ void pair_eval(const WenoK& K, const T (&a)[7], const T (&b)[7], int xa, int xb, double& WA, double& WB) {
+#ifndef LSM_NO_F32X2
+    if constexpr (sizeof(T) == 4) {
+        // Float32: both nodes in one packed evaluation (uniform directions); differences lane-wise, shared ones by value numbering
+        if ((xa | xb) >= 0) {
+            weno_core2(f2(a[1] - a[0], b[1] - b[0]), f2(a[2] - a[1], b[2] - b[1]), f2(a[3] - a[2], b[3] - b[2]), f2(a[4] - a[3], b[4] - b[3]),
+                       f2(a[5] - a[4], b[5] - b[4]), WA, WB);
+            return;
+        }
+        if ((xa & xb) < 0) {
+            weno_core2(f2(a[6] - a[5], b[6] - b[5]), f2(a[5] - a[4], b[5] - b[4]), f2(a[4] - a[3], b[4] - b[3]), f2(a[3] - a[2], b[3] - b[2]),
+                       f2(a[2] - a[1], b[2] - b[1]), WA, WB);
+            return;
+        }
+    }
+#endif
     if ((xa | xb) >= 0) {                 // both minus-biased: D-(I-2 .. I+2) = first differences -3 .. 1
         WA = weno_core<XMAX>(K, T(a[1] - a[0]), T(a[2] - a[1]), T(a[3] - a[2]), T(a[4] - a[3]), T(a[5] - a[4]));
         WB = weno_core<XMAX>(K, T(b[1] - b[0]), T(b[2] - b[1]), T(b[3] - b[2]), T(b[4] - b[3]), T(b[5] - b[4]));
