@@ -101,6 +101,8 @@ __device__ __forceinline__ void pair_eval_n(const WenoK& K, const double (&a)[7]
     }
 }
 
+constexpr int PAIR_EIK = 100;    // value of the CK template parameter that selects the Eikonal variant
+
 // CK: COEF_FIELD (stored velocity, staged by TMA next to the phi ring) or COEF_SEPARABLE (u_d = s_d X_d[i] Y_d[j] Z_d[k] from tables).
 // SB: static RK base mode (SB_* of lsm_tile_util.cuh).  FCFL: also reduce the next step's CFL maximum (see StageParams).
 template <class T, int RY, int NT, int CK, bool FCFL, int SB, bool ISO, bool XMAX, bool HASN>
@@ -113,11 +115,14 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
     constexpr bool HAS_OUT2 = SB == SB_IN_OUT2;
     // HASN: the term list is (NormalMotionTerm(stored speed), AdvectionTerm(stored velocity, WENO5)) — BASELINE config 5; else the
     // single advection term.  Aux tiles: [speed,] u1, u2, u3 [, phi^n]
+    // CK == PAIR_EIK: the single term is EikonalReinitializationTerm with a frozen, stored S0 (BASELINE config 4): aux tiles S0 [, phi^n]
+    constexpr bool EIK = CK == PAIR_EIK;
     constexpr int TA = HASN ? 1 : 0;                       // index of the advection term
     constexpr int AU = HASN ? 1 : 0;                       // first velocity tile
-    constexpr int NVEL = (CK == COEF_FIELD ? 3 : 0) + AU;  // tiles before phi^n
+    constexpr int NVEL = EIK ? 1 : (CK == COEF_FIELD ? 3 : 0) + AU;  // tiles before phi^n
     constexpr int NAUX = NVEL + (HAS_P0 ? 1 : 0);
     static_assert(!HASN || (CK == COEF_FIELD && !FCFL && sizeof(T) == 8 && RY == 1), "the two-term variant is Float64, stored coefficients");
+    static_assert(!EIK || (!HASN && !FCFL && RY == 1), "the Eikonal variant is a single term without fused CFL");
     constexpr unsigned PHI_BYTES = (unsigned)(W * G::HH * sizeof(T));
     constexpr unsigned AUX_BYTES = (unsigned)(NAUX * TILE * sizeof(T));
 
@@ -267,7 +272,61 @@ pair3d_kernel(const __grid_constant__ StageParams<T> P, const __grid_constant__ 
 
         const unsigned cur = sc_a + (unsigned)zo[HAL];
         const unsigned auxz = st_a + (unsigned)ab;
-        if (act[0]) {
+        if constexpr (EIK) {
+            if (act[0]) {
+                // EikonalReinitializationTerm, frozen sign (levelsetterms.jl:234-265, O&F 7.5): H = S0 (|grad phi|_Godunov - 1) with the
+                // second-order ENO pair of every dimension; the operations are those of lsm_tiled.cu (direct second differences:
+                // C4 is the rounding-sensitive configuration), evaluated for the two nodes of the thread from 128-bit loads.
+                const V2 xm = lds_pair(cur - 2 * ES, T()), c0 = lds_pair(cur, T()), xp = lds_pair(cur + 2 * ES, T());
+                const V2 s0 = lds_pair(auxz, T());
+                const double cf[2] = {double(s0.x), double(s0.y)};
+                const bool sp[2] = {cf[0] > 0, cf[1] > 0};
+                double gsel[2] = {0.0, 0.0};
+                auto eno2 = [&](T pm2, T pm1, T qc, T pp1, T pp2, double w, bool spc, double& acc) {
+                    const double dm = double(T(qc - pm1)), dp = double(T(pp1 - qc));
+                    const double c2 = double(T(pp1 - T(2) * qc + pm1));
+                    const double cm = double(T(pm2 - T(2) * pm1 + qc)), cp = double(T(qc - T(2) * pp1 + pp2));
+                    const double ng = fma(0.5, minmod(cm, c2), dm);
+                    const double ps = fma(-0.5, minmod(cp, c2), dp);
+                    const double a = ((ng > 0) == spc) ? ng : 0.0;
+                    const double b = ((ps < 0) == spc) ? ps : 0.0;
+                    acc = fma(fma(a, a, b * b), w, acc);
+                };
+                // x: nodes i (c0.x) and i+1 (c0.y)
+                eno2(xm.x, xm.y, c0.x, c0.y, xp.x, ihsq[0], sp[0], gsel[0]);
+                eno2(xm.y, c0.x, c0.y, xp.x, xp.y, ihsq[0], sp[1], gsel[1]);
+                {   // y
+                    const V2 a2 = lds_pair(cur - 2 * W * ES, T()), a1 = lds_pair(cur - W * ES, T()), b1 = lds_pair(cur + W * ES, T()), b2 = lds_pair(cur + 2 * W * ES, T());
+                    eno2(a2.x, a1.x, c0.x, b1.x, b2.x, ihsq[1], sp[0], gsel[0]);
+                    eno2(a2.y, a1.y, c0.y, b1.y, b2.y, ihsq[1], sp[1], gsel[1]);
+                }
+                {   // z
+                    const V2 a2 = lds_pair(sc_a + (unsigned)zo[HAL - 2], T()), a1 = lds_pair(sc_a + (unsigned)zo[HAL - 1], T()),
+                             b1 = lds_pair(sc_a + (unsigned)zo[HAL + 1], T()), b2 = lds_pair(sc_a + (unsigned)zo[HAL + 2], T());
+                    eno2(a2.x, a1.x, c0.x, b1.x, b2.x, ihsq[2], sp[0], gsel[0]);
+                    eno2(a2.y, a1.y, c0.y, b1.y, b2.y, ihsq[2], sp[1], gsel[1]);
+                }
+                T xb[2] = {c0.x, c0.y};
+                if (HAS_P0) {
+                    const V2 pn = lds_pair(auxz + TILE * ES, T());
+                    const T pv[2] = {pn.x, pn.y};
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (SB == SB_S2) xb[c] = T(fma(0.75, double(pv[c]), 0.25 * double(xb[c])));
+                        else if (SB == SB_S3) xb[c] = div3(T(pv[c] + T(2) * xb[c]));
+                        else xb[c] = pv[c];
+                    }
+                }
+                V2 o, o2;
+                const double h0 = cf[0] * (sqrt(gsel[0]) - 1.0), h1 = cf[1] * (sqrt(gsel[1]) - 1.0);
+                o.x = T(fma(-P.c, h0, double(xb[0]))); o.y = T(fma(-P.c, h1, double(xb[1])));
+                *reinterpret_cast<V2*>(P.out + lin) = o;
+                if (HAS_OUT2) {
+                    o2.x = T(fma(-P.c2, h0, double(c0.x))); o2.y = T(fma(-P.c2, h1, double(c0.y)));
+                    *reinterpret_cast<V2*>(P.out2 + lin) = o2;
+                }
+            }
+        } else if (act[0]) {
             double H[RY][2];
             double uraw[RY][2][3];
             V2 cc[RY];
@@ -467,7 +526,7 @@ cudaError_t launch_pair_x(const StageParams<T>& P, const AuxList& A, cudaStream_
     using G = PairGeom<T, RY, NT>;
     auto kern = pair3d_kernel<T, RY, NT, CK, FCFL, SB, ISO, XMAX, HASN>;
     constexpr bool HAS_P0 = SB == SB_S2 || SB == SB_S3 || SB == SB_P0;
-    constexpr int NAUX = (CK == COEF_FIELD ? 3 : 0) + (HASN ? 1 : 0) + (HAS_P0 ? 1 : 0);
+    constexpr int NAUX = (CK == PAIR_EIK ? 1 : (CK == COEF_FIELD ? 3 : 0) + (HASN ? 1 : 0)) + (HAS_P0 ? 1 : 0);
     const size_t smem = G::smem_bytes(NAUX);
     static size_t attr_smem[16] = {};
     { cudaError_t e = ensure_dyn_smem(kern, smem, attr_smem); if (e != cudaSuccess) return e; }
@@ -494,6 +553,7 @@ cudaError_t launch_pair_x(const StageParams<T>& P, const AuxList& A, cudaStream_
 
 template <class T, int CK, bool FCFL, int SB, bool HASN>
 cudaError_t launch_pair(const StageParams<T>& P, const AuxList& A, cudaStream_t s, bool exact_eps) {
+    if constexpr (CK == PAIR_EIK) return launch_pair_x<T, CK, FCFL, SB, false, false, false>(P, A, s);
     const bool iso = P.h[0] == P.h[1] && P.h[1] == P.h[2];
     if (sizeof(T) == 4 || !exact_eps)      // (the Float32 evaluation normalises by the exact FP32 maximum either way)
         return iso ? launch_pair_x<T, CK, FCFL, SB, true, false, HASN>(P, A, s) : launch_pair_x<T, CK, FCFL, SB, false, false, HASN>(P, A, s);
@@ -504,7 +564,7 @@ cudaError_t launch_pair(const StageParams<T>& P, const AuxList& A, cudaStream_t 
 
 template <class T, int CK, bool FCFL, bool HASN = false>
 cudaError_t launch_pair_sb(const StageParams<T>& P, const AuxList& A, cudaStream_t s, bool exact_eps) {
-    constexpr int SP0 = (CK == COEF_FIELD ? 3 : 0) + (HASN ? 1 : 0);
+    constexpr int SP0 = CK == PAIR_EIK ? 1 : (CK == COEF_FIELD ? 3 : 0) + (HASN ? 1 : 0);
     if (A.p0 >= 0 && A.p0 != SP0) return cudaErrorNotSupported;
     if (P.base == BASE_IN && !P.p0) {
         if (!P.out2) return launch_pair<T, CK, FCFL, SB_IN, HASN>(P, A, s, exact_eps);
@@ -525,7 +585,8 @@ cudaError_t launch_stage_pair3d(const StageParams<T>& P, const AuxList& A, cudaS
     if (pair_kernel_disabled() || tma_disabled() || !encode_tiled_fn()) return cudaErrorNotSupported;
     if (P.nterms != 1 && P.nterms != 2) return cudaErrorNotSupported;
     const TermDev& ta = P.terms[P.nterms - 1];          // the advection term (last)
-    if (ta.kind != TERM_ADVECTION || ta.scheme != SCHEME_WENO5) return cudaErrorNotSupported;
+    const bool eik = P.nterms == 1 && ta.kind == TERM_EIKONAL && ta.coef_kind == COEF_FIELD && !ta.coef_f64 && A.first[0] == 0 && !P.cfl_out;
+    if (!eik && (ta.kind != TERM_ADVECTION || ta.scheme != SCHEME_WENO5)) return cudaErrorNotSupported;
     const View<T>& v = P.in;
     if ((v.n[0] * sizeof(T)) % 16 != 0 || v.n[0] < 8 || v.n[1] < 8 || v.n[2] < 4) return cudaErrorNotSupported;
     if ((long)v.n[0] * v.n[1] >= (1L << 31)) return cudaErrorNotSupported;
@@ -535,6 +596,7 @@ cudaError_t launch_stage_pair3d(const StageParams<T>& P, const AuxList& A, cudaS
             const bool index_map = b.kind == BC_PERIODIC || b.kind == BC_SYMMETRY || (b.kind == BC_EXTRAP && b.P == 0) || (b.kind == BC_HALO && d == 2);
             if (!index_map) return cudaErrorNotSupported;
         }
+    if (eik) return launch_pair_sb<T, PAIR_EIK, false>(P, A, s, exact_eps);
     if (P.nterms == 2) {
         // (NormalMotionTerm(stored speed), AdvectionTerm(stored velocity)) in this order, Float64, no fused CFL
         if constexpr (sizeof(T) == 8) {

@@ -623,7 +623,7 @@ cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, 
         }
     }
     if (P.p0) { A.p0 = A.n; A.src[A.n++] = P.p0; }
-    if (pair_mode && ndim == 3 && (mask == M_ADV_WENO || (mask == (M_NORMAL | M_ADV_WENO) && P.nterms == 2))) {      // headline path: x-pair kernel (lsm_pair3d.cu); falls through when it does not apply
+    if (pair_mode && ndim == 3 && (mask == M_ADV_WENO || (mask == (M_NORMAL | M_ADV_WENO) && P.nterms == 2) || (mask == M_EIK && P.nterms == 1))) {      // headline path: x-pair kernel (lsm_pair3d.cu); falls through when it does not apply
         const cudaError_t e = launch_stage_pair3d<T>(P, A, s, pair_mode == 2);
         if (e != cudaErrorNotSupported) { if (used_pair) *used_pair = 1; return e; }
     }

@@ -374,6 +374,34 @@ def test_pair2d_kernel_vs_tiled(m, n):
                 assert d <= (1e-13 if dtype == np.float64 else 1e-6), (n, bc, np.dtype(dtype).name, curv, integ.__name__, d)
 
 
+@pytest.mark.parametrize("n", [(128, 64, 40), (72, 52, 37), (64, 8, 8)], ids=["128x64x40", "72x52x37", "64x8x8"])
+def test_pair_kernel_eikonal_bitwise_vs_tiled(m, n):
+    """BASELINE config 4's term (EikonalReinitializationTerm with a frozen stored S0) through the x-pair kernel: the same
+    operations as the general tiled kernel (direct second differences), so the states must be BIT-IDENTICAL — partial tiles,
+    every index-map BC, FE / RK2 / RK3."""
+    ctx = m.default_context()
+    lc, hc = (-1, -1, -1), (1, 1, 1)
+    x, y, z = H.coords(lc, hc, n)
+    r = np.sqrt(x * x + y * y + z * z)
+    phi = (r - 0.5) * (1 + 0.4 * np.sin(3 * np.pi * x) * np.sin(3 * np.pi * y) * np.sin(3 * np.pi * z))
+    for k, bc in enumerate(PAIR_BCS):
+        case = H.Case("P4", lc, hc, n, phi, [dict(kind="eikonal", frozen=True)], bc, np.float64)
+        integ = (m.RK3, m.RK2, m.ForwardEuler)[k % 3]
+        outs = []
+        for kernel in (0, 3):
+            ctx.set_option(OPT_KERNEL, kernel)
+            ctx.reset_counters()
+            f = case.engine_field(m)
+            eq = m.LevelSetEquation(terms=case.engine_terms(m, f), ic=f, integrator=integ())
+            dt = 0.5 * m.compute_cfl(eq.terms, eq.state, 0.0)
+            m.integrate(eq, 5 * dt * (1 - 1e-12))
+            outs.append((eq.t, eq.steps_taken, eq.state.peek().copy(), ctx.counters()["pair_launches"]))
+        ctx.set_option(OPT_KERNEL, 0)
+        assert outs[0][3] > 0 and outs[1][3] == 0, "kernel selection"
+        assert outs[0][:2] == outs[1][:2]
+        assert np.array_equal(outs[0][2], outs[1][2]), (n, bc, integ.__name__, float(np.abs(outs[0][2] - outs[1][2]).max()))
+
+
 def _notched_sphere_case(n, dtype=np.float64):
     """3-D Zalesak-type body (sphere with a slot: kinks along the slot edges) in the Enright velocity: the sharp-feature
     counterpart of C3 for the x-pair kernel."""
