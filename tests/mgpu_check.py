@@ -40,6 +40,8 @@ def main():
     c = H.c3_enright(nc); cases.append(("C3 WENO5 advection x cos (fused CFL), Neumann", c, "RK3", 8))
     c = H.c5_normal_advection(nc); cases.append(("C5 normal motion + advection", c, "RK3", 6))
     c = H.c4_eikonal(nc); cases.append(("C4 eikonal RK2", c, "RK2", 6))
+    # 2-D, decomposed along y: on 2 ranks every slab is large enough for the 2-D x-pair kernel (rows arrive through the halo rows)
+    c = H.c2_zalesak_curvature(768); cases.append(("C2 2-D Zalesak advection + curvature", c, "RK3", 5))
     # uneven slabs + periodic wrap across ranks (node n duplicates node 1) + extrapolation in y
     lc, hc, n = (-1, -1, -1), (1, 1, 1), (20, 18, nz)
     X = H.coords(lc, hc, n)
