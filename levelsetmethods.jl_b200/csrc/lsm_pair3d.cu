@@ -545,7 +545,8 @@ cudaError_t launch_pair_x(const StageParams<T>& P, const AuxList& A, cudaStream_
     int nchunks = std::max(1, (nr + 32) / 64);
     const long want = (2L * 296 + tiles - 1) / tiles;                  // chunks needed for ~2 waves
     if (nchunks < want) nchunks = (int)std::min<long>(want, std::max(1, nr / 8));
-    const int cz = (nr + nchunks - 1) / nchunks;
+    static const int cz_env = [] { const char* e = getenv("LSM_B200_CZ"); return e ? atoi(e) : 0; }();     // experiments only
+    const int cz = cz_env > 0 ? std::min(cz_env, nr) : (nr + nchunks - 1) / nchunks;
     dim3 block(32, NT / 32), grid((v.n[0] + G::BX - 1) / G::BX, (v.n[1] + G::BY - 1) / G::BY, (nr + cz - 1) / cz);
     kern<<<grid, block, smem, s>>>(P, A, M, cz);
     return cudaGetLastError();
