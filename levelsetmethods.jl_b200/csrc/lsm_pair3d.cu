@@ -1,5 +1,5 @@
-// lsm_pair3d.cu — the headline kernel: one fused RK stage of 3-D WENO5 advection (BASELINE configs 3 and the
-// single-term Float32/Float64 3-D advection runs), re-designed around the measured issue model of round 1
+// lsm_pair3d.cu — the headline kernel: one fused RK stage of 3-D WENO5 advection (BASELINE config 3 and, in its variants,
+// configs 4 and 5), re-designed around the measured issue model of round 1
 // (a Float64 instruction costs two issue slots, everything else one, and the kernel is issue bound):
 //
 //   * every thread owns TWO ADJACENT x nodes (i, i+1) of one row (RY = 1) or of two adjacent rows (RY = 2) and
@@ -16,9 +16,15 @@
 //     boundaryconditions.jl:107-153) are fetched from their remapped global address while plane z is being
 //     computed and stored before the barrier.  Ghost planes in z are whole-plane index remaps of the TMA coordinate.
 //
-// The arithmetic is the SAME sequence of operations as lsm_tiled.cu's weno5_up / stage combination, so the two
-// kernels agree bit for bit (tests/test_gpu_parity.py::test_pair_kernel_bitwise_vs_tiled) and both stay within
-// 1e-10 of the oracle after 100 RK3 steps.
+// Variants (template parameters): CK = stored / separable velocity, or PAIR_EIK = the frozen-sign EikonalReinitializationTerm of
+// BASELINE config 4; HASN = NormalMotionTerm + AdvectionTerm (config 5: the ENO2 pair of the Godunov norm and WENO5 share the
+// first / second differences of a node); ISO = equal mesh size (per-dimension scaling folded into the stage coefficient);
+// XMAX = exact max|d| for the WENO epsilon instead of the 20-bit one (lsm_tile_util.cuh: absmax5_hi); Float32 fields evaluate
+// the two nodes with packed FFMA2 / FADD2 / FMUL2 (lsm_pair_common.cuh: weno_core2).
+//
+// With XMAX the arithmetic is the SAME sequence of operations as lsm_tiled.cu's weno5_up / eno2 / stage combination, so the two
+// kernels agree bit for bit (tests/test_gpu_parity.py::test_pair_kernel_bitwise_vs_tiled, ::test_pair_kernel_eikonal_bitwise_vs_tiled);
+// the default (20-bit epsilon maximum) stays within 1e-13 of that and within 1e-10 of the oracle after 100 RK3 steps.
 #include <algorithm>
 #include "lsm_pair_common.cuh"
 
