@@ -20,12 +20,22 @@
 #include "lsm_dev.cuh"
 #include "lsm_kernels.h"
 #include "nccl_dyn.h"
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges are no-ops unless a profiler injects itself
 
 using namespace lsm;
 
 namespace {
 
 thread_local std::string g_err;
+
+// NVTX ranges around the step loop, every RK stage and the halo exchange: visible in Nsight Systems timelines,
+// free otherwise.  LSM_B200_NVTX=0 turns even the (tiny) call overhead off.
+struct NvtxRange {
+    static bool enabled() { static const bool on = [] { const char* e = getenv("LSM_B200_NVTX"); return !(e && *e == '0'); }(); return on; }
+    bool on;
+    explicit NvtxRange(const char* name) : on(enabled()) { if (on) nvtxRangePushA(name); }
+    ~NvtxRange() { if (on) nvtxRangePop(); }
+};
 
 int32_t fail(int32_t code, const char* fmt, ...) {
     char buf[512];
@@ -290,6 +300,7 @@ int32_t make_term_dev(const lsm_field* phi, const lsm_term& t, double g, TermDev
 int32_t exchange_halo(lsm_field* f, cudaStream_t s) {
     lsm_ctx* c = f->ctx;
     if (c->nranks == 1 || !f->halo) { f->halo_valid = true; return LSM_OK; }
+    NvtxRange nvtx("lsm halo exchange");
     const int last = f->ndim - 1;
     const bool periodic = f->bc[last][0].kind == LSM_BC_PERIODIC;
     const size_t es = esize(f->dtype);
@@ -358,6 +369,7 @@ int32_t launch_stage_range(lsm_ctx* c, int ndim, StageParams<T>& P, int r0, int 
 template <class T>
 int32_t run_stage_t(lsm_ctx* c, lsm_field* in, lsm_field* p0, lsm_field* out, lsm_field* out2, int base, double cc, double c2,
                     const lsm_term* terms, int nterms, double tstage, const double* gscale, bool out_needs_halo) {
+    NvtxRange nvtx("lsm RK stage");
     StageParams<T> P{};
     P.in = make_view<T>(in);
     P.p0 = p0 ? static_cast<const T*>(p0->p) : nullptr;
@@ -1176,6 +1188,7 @@ int32_t lsm_integrate(lsm_ctx* ctx, int32_t integrator, double cfl, lsm_field* p
                       int32_t nterms, double t0, double tf, double dt_max, int64_t max_steps,
                       double* t_out, int64_t* steps_out) {
     TRY(check_state(ctx, phi, terms, nterms));
+    NvtxRange nvtx("lsm_integrate");
     if (integrator < LSM_FORWARD_EULER || integrator > LSM_RK3) return fail(LSM_ERR_ARG, "bad integrator %d", integrator);
     if (!(tf >= t0))     // levelsetequation.jl:196
         return fail(LSM_ERR_TIME, "final time %g must be >= initial time %g: the level-set equation cannot be solved back in time", tf, t0);
