@@ -5,7 +5,7 @@ Workload (N = 1): BASELINE.json configs[2] "C3": 3-D sphere SDF in the Enright/L
 velocity (stored Float64 velocity field x cos(pi t / 3)), 512^3 nodes, WENO5 + TVD-RK3, NeumannBC.
 One bench "step" = one RK3 step of integrate! = CFL reduction + 3 fused stage kernels.
 N > 1: the same workload weak-scaled — every rank owns a 512 x 512 x 512 slab of a 512 x 512 x (512 N)
-grid, 3-plane halos exchanged over NCCL each stage ("scaling": "weak").
+grid of cubic cells, 3-plane halos exchanged over NCCL each stage ("scaling": "weak").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--n 512] [--impl reference]
     torchrun --nproc-per-node N ... bench.py --gpus N ...
@@ -53,8 +53,16 @@ def enright_tables(n, nz_glob, lz):
 
 def build_c3(m, ctx, n, G):
     """C3 with every field generated on the device (lsm_field_fill_shape / lsm_field_fill_separable): phi0 = |x - 0.35| - 0.15,
-    stored Float64 Enright velocity x cos(pi t / 3).  N ranks: an n x n x (n N) grid on (0,0,0)..(1,1,N), one n^3 slab per rank."""
-    nz, lz = n * G, float(G)
+    stored Float64 Enright velocity x cos(pi t / 3).  N ranks: an n x n x (n N) grid of cubic cells, one n^3 slab per rank."""
+    # cubic cells at every N: the domain is (0,0,0)..(1,1,lz) with lz = (nz - 1) h_x, so that h_z == h_x exactly (the isotropic-mesh
+    # instantiation of the stage kernel runs at N > 1 as it does at N = 1)
+    nz = n * G
+    hx = 1.0 / (n - 1)
+    lz = (nz - 1) * hx
+    for _ in range(8):
+        if lz / (nz - 1) == hx:
+            break
+        lz = float(np.nextafter(lz, lz + 1 if lz / (nz - 1) < hx else lz - 1))
     grid = m.CartesianGrid((0, 0, 0), (1, 1, lz), (n, n, nz))
     phi = m.MeshField.from_shape(grid, "sphere", (0.35, 0.35, 0.35, 0.15), bc=m.NeumannBC(), ctx=ctx)
     sc, tabs = enright_tables(n, nz, lz)
