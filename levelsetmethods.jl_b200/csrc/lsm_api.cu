@@ -412,13 +412,16 @@ int32_t run_stage_t(lsm_ctx* c, lsm_field* in, lsm_field* p0, lsm_field* out, ls
         // ships them (NCCL send/recv) while the interior is still being computed.  The next stage waits for both.
         CU(cudaEventRecord(c->ev_main, c->stream));                 // everything enqueued so far (previous stage, halos, memsets)
         CU(cudaStreamWaitEvent(c->bstream, c->ev_main, 0));
-        TRY(launch_stage_range<T>(c, in->ndim, P, 0, HALO + 1, c->bstream));
-        TRY(launch_stage_range<T>(c, in->ndim, P, nl - HALO - 1, nl, c->bstream));
+        // the slabs hold exactly the planes exchange_halo ships: HALO planes per side, one more when the decomposed axis is periodic
+        // (the wrap-around partner receives planes 1..3 / nl-4..nl-2, boundaryconditions.jl:107-119)
+        const int sl = HALO + (in->bc[last][0].kind == LSM_BC_PERIODIC ? 1 : 0);
+        TRY(launch_stage_range<T>(c, in->ndim, P, 0, sl, c->bstream));
+        TRY(launch_stage_range<T>(c, in->ndim, P, nl - sl, nl, c->bstream));
         CU(cudaEventRecord(c->ev_boundary, c->bstream));
         CU(cudaStreamWaitEvent(c->comm, c->ev_boundary, 0));
         TRY(exchange_halo(out, c->comm));
         CU(cudaEventRecord(c->ev_halo, c->comm));
-        TRY(launch_stage_range<T>(c, in->ndim, P, HALO + 1, nl - HALO - 1));
+        TRY(launch_stage_range<T>(c, in->ndim, P, sl, nl - sl));
         CU(cudaStreamWaitEvent(c->stream, c->ev_boundary, 0));
         CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
     } else {
