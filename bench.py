@@ -265,7 +265,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=0, help="nodes per axis (c3: per GPU, default 512; c5: global, default 1024)")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=0,
+                    help="nodes per axis (c3: per GPU, default 512; c5: global, default 1024); use --size under torchrun, whose own parser\n"
+                         "rejects --n as an ambiguous abbreviation of --nnodes / --nproc-per-node")
     ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
                     help="c3 = headline (weak-scaled Enright advection); c5 = BASELINE configs[4], strong-scaled 1024^3 normal motion + advection")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
