@@ -92,6 +92,7 @@ typedef struct {
     double  sum_stage_ms;     /* accumulated over timed stages since lsm_reset_counters */
     int64_t timed_stages;
     int64_t pair_launches;    /* stage launches that took the x-pair kernel (3-D single-term WENO5 advection)  */
+    int64_t resident_steps;   /* time steps taken inside the resident cluster kernel (small 2-D grids; one launch per lsm_integrate) */
 } lsm_counters;
 
 /* options for lsm_set_option */
@@ -103,8 +104,11 @@ enum {
     LSM_OPT_OVERLAP = 3,      /* 1 (default): overlap halo exchange with interior compute (multi-rank)        */
     LSM_OPT_FUSE_CFL = 4,     /* 1 (default): lsm_integrate lets the last RK stage reduce the next step's CFL maximum (time-scaled stored velocity) */
     LSM_OPT_GRAPH = 5,        /* 1 (default): lsm_integrate replays a captured CUDA graph of one step's stage launches on small grids (launch-bound regime) */
-    LSM_OPT_CFL_CANDIDATES = 6 /* 1 (default): the CFL maximum of a TIME-SCALED static coefficient field is evaluated on the host over the few nodes that
+    LSM_OPT_CFL_CANDIDATES = 6, /* 1 (default): the CFL maximum of a TIME-SCALED static coefficient field is evaluated on the host over the few nodes that
                                   can attain it for any scale (exact, see lsm_api.cu) - no reduction pass, D2H or host sync per step */
+    LSM_OPT_RESIDENT = 7      /* 1 (default): lsm_integrate runs the whole time loop of a small 2-D grid (<= 2^15 nodes, one stored-velocity WENO5
+                                 advection term without a time factor, index-map BCs) in ONE cluster kernel that keeps the state in distributed
+                                 shared memory (lsm_resident2d.cu); bit-identical to the per-stage kernels */
 };
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */

@@ -23,7 +23,7 @@ COEF_CONST, COEF_FIELD, COEF_SEPARABLE, COEF_NONE = 0, 1, 2, 3
 TS_NONE, TS_COS, TS_HOST = 0, 1, 2
 SHAPE_SPHERE, SHAPE_BOX, SHAPE_PLANE, SHAPE_CONST = 0, 1, 2, 3
 FORWARD_EULER, RK2, RK3 = 0, 1, 2
-OPT_KERNEL, OPT_TIME_STAGES, OPT_CFL_CACHE, OPT_OVERLAP, OPT_FUSE_CFL, OPT_GRAPH, OPT_CFL_CANDIDATES = 0, 1, 2, 3, 4, 5, 6
+OPT_KERNEL, OPT_TIME_STAGES, OPT_CFL_CACHE, OPT_OVERLAP, OPT_FUSE_CFL, OPT_GRAPH, OPT_CFL_CANDIDATES, OPT_RESIDENT = 0, 1, 2, 3, 4, 5, 6, 7
 MAX_TERMS = 4
 
 
@@ -40,7 +40,7 @@ class lsm_counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("stage_launches", C.c_int64), ("cfl_passes", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("halo_bytes_sent", C.c_int64),
                 ("last_stage_ms", C.c_double), ("sum_stage_ms", C.c_double), ("timed_stages", C.c_int64),
-                ("pair_launches", C.c_int64)]
+                ("pair_launches", C.c_int64), ("resident_steps", C.c_int64)]
 
 
 class LSMError(RuntimeError):

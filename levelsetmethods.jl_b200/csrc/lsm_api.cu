@@ -90,6 +90,7 @@ struct lsm_ctx {
     std::vector<CflCacheEntry> cfl_cache;
     std::vector<CflCand> cfl_cand;
     int opt_cand = 1;           // LSM_OPT_CFL_CANDIDATES
+    int opt_resident = 1;       // LSM_OPT_RESIDENT
     int stage_skip_zero_u = 0;  // transient: set by lsm_extend_along_normals around its stages (StageParams::skip_zero_u)
     unsigned* d_cand_count = nullptr; double* d_cand = nullptr; double* h_cand = nullptr;   // candidate staging (device / pinned)
     void* stage[2] = {nullptr, nullptr};        // AoS <-> SoA staging chunks of vector-field transfers (allocated on first use)
@@ -480,6 +481,54 @@ int32_t stage_impl(lsm_ctx* ctx, int integ, int stage, lsm_field* phi, const lsm
 }
 
 int nstages(int integ) { return integ == LSM_FORWARD_EULER ? 1 : integ == LSM_RK2 ? 2 : 3; }
+
+// lsm_resident2d.cu covers: single rank, 2-D, ONE AdvectionTerm(stored velocity of the state's dtype, WENO5) without a time factor,
+// index-map boundary conditions (periodic / Neumann / symmetry), automatic kernel selection, no per-stage timing
+bool resident_eligible(const lsm_ctx* ctx, const lsm_field* phi, const lsm_term* terms, int nterms) {
+    if (!ctx->opt_resident || ctx->nranks != 1 || ctx->opt_time || ctx->opt_kernel != 0) return false;
+    if (phi->ndim != 2 || nterms != 1) return false;
+    const lsm_term& t = terms[0];
+    if (t.kind != LSM_TERM_ADVECTION || t.scheme != LSM_WENO5 || t.coef_kind != LSM_COEF_FIELD || t.tscale_kind != LSM_TS_NONE) return false;
+    if (!t.field || t.field->separable || t.field->dtype != phi->dtype || t.field->ncomp != 2 || t.field->ctx != ctx) return false;
+    for (int d = 0; d < 2; ++d) {
+        if (t.field->nglob[d] != phi->nglob[d]) return false;
+        for (int sd = 0; sd < 2; ++sd) {
+            const int k = phi->bc[d][sd].kind;
+            if (!(k == LSM_BC_PERIODIC || k == LSM_BC_SYMMETRY || (k == LSM_BC_EXTRAP && phi->bc[d][sd].P == 0))) return false;
+        }
+    }
+    return phi->dtype == LSM_F64 ? resident2d_supported<double>(phi->n[0], phi->n[1]) : resident2d_supported<float>(phi->n[0], phi->n[1]);
+}
+
+template <class T>
+int32_t run_resident(lsm_ctx* ctx, int integ, lsm_field* phi, const lsm_term& term, const std::vector<std::pair<double, long>>& runs) {
+    NvtxRange nvtx("lsm resident time loop");
+    ResidentArgs<T> R{};
+    R.phi = static_cast<const T*>(phi->p);
+    R.out = static_cast<T*>(phi->p);
+    const lsm_field* u = term.field;
+    for (int d = 0; d < 2; ++d) {
+        R.u[d] = static_cast<const T*>(u->p) + (size_t)d * u->cstride;
+        R.n[d] = phi->n[d]; R.h[d] = phi->h[d];
+        for (int sd = 0; sd < 2; ++sd) R.bc[d][sd] = phi->bc[d][sd].kind;
+    }
+    R.s1 = phi->n[0];
+    R.nstages = nstages(integ);
+    R.wk = weno_constants();
+    int64_t done = 0;
+    for (size_t i = 0; i < runs.size(); i += 4) {
+        R.nruns = (int)std::min<size_t>(4, runs.size() - i);
+        int64_t here = 0;
+        for (int k = 0; k < R.nruns; ++k) { R.dt[k] = runs[i + k].first; R.count[k] = runs[i + k].second; here += runs[i + k].second; }
+        cudaError_t e = launch_resident2d<T>(R, ctx->stream);
+        if (e == cudaErrorNotSupported && done == 0) return LSM_ERR_UNSUPPORTED;          // nothing has run: the caller takes the regular path
+        if (e != cudaSuccess) return fail(LSM_ERR_CUDA, "resident kernel launch failed: %s", cudaGetErrorString(e));
+        done += here;
+        ctx->cnt.kernel_launches += 1; ctx->cnt.resident_steps += here;
+    }
+    phi->version++; phi->halo_valid = true;
+    return LSM_OK;
+}
 
 unsigned long long dbits(double s) {
     unsigned long long b;
@@ -885,6 +934,7 @@ int32_t lsm_set_option(lsm_ctx* c, int32_t option, int32_t value) {
         case LSM_OPT_TIME_STAGES: c->opt_time = value != 0; break;
         case LSM_OPT_CFL_CACHE: c->opt_cfl_cache = value != 0; c->cfl_cache.clear(); c->cfl_cand.clear(); break;
         case LSM_OPT_CFL_CANDIDATES: c->opt_cand = value != 0; c->cfl_cand.clear(); break;
+        case LSM_OPT_RESIDENT: c->opt_resident = value != 0; break;
         case LSM_OPT_OVERLAP: c->opt_overlap = value != 0; break;
         case LSM_OPT_FUSE_CFL: c->opt_fuse_cfl = value != 0; break;
         case LSM_OPT_GRAPH: c->opt_graph = value != 0; break;
@@ -1210,6 +1260,31 @@ int32_t lsm_integrate(lsm_ctx* ctx, int32_t integrator, double cfl, lsm_field* p
     double gdt = 0.0;
     lsm_counters gdelta{};          // counters of one captured step
     uint64_t gver[3] = {0, 0, 0};   // version bumps of phi / buf1 / buf2 per step
+    // Small 2-D grids (the reference's CPU-sized cases): the whole time loop runs in ONE cluster kernel that keeps the state, the
+    // stage buffers and the velocity in distributed shared memory (lsm_resident2d.cu).  The step sizes of a static velocity are
+    // known in advance: dt = min(dt_max, cfl * dt_cfl, tf - tc) with a constant dt_cfl (timestepping.jl:104-118), so the host replays
+    // the loop's arithmetic and hands the kernel the run-length encoded sequence.  Whatever is left (max_steps, more than
+    // RES_STEP_CAP steps, a launch that is not possible) is done by the regular loop below.
+    if (resident_eligible(ctx, phi, terms, nterms) && tc <= tf - jl_eps(tc) && (max_steps < 0 || max_steps > 0)) {
+        double dt_cfl;
+        rc = compute_cfl_impl(ctx, phi, terms, nterms, tc, nullptr, &dt_cfl);
+        if (rc != LSM_OK) { if (t_out) *t_out = tc; if (steps_out) *steps_out = 0; return rc; }
+        const double D = jl_min(dt_max, cfl * dt_cfl);
+        if (std::isfinite(D) && D > 0.0) {
+            constexpr int64_t RES_STEP_CAP = 1 << 22;
+            std::vector<std::pair<double, long>> runs;
+            double t = tc; int64_t n = 0;
+            while (t <= tf - jl_eps(t) && n < RES_STEP_CAP && (max_steps < 0 || n < max_steps)) {
+                const double dt = jl_min(D, tf - t);                       // timestepping.jl:111
+                if (!runs.empty() && runs.back().first == dt) runs.back().second++; else runs.emplace_back(dt, 1L);
+                t += dt; ++n;
+            }
+            int32_t rr = phi->dtype == LSM_F64 ? run_resident<double>(ctx, integrator, phi, terms[0], runs)
+                                               : run_resident<float>(ctx, integrator, phi, terms[0], runs);
+            if (rr == LSM_OK) { tc = t; steps = n; }
+            else if (rr != LSM_ERR_UNSUPPORTED) { if (t_out) *t_out = tc; if (steps_out) *steps_out = 0; return rr; }
+        }
+    }
     while (tc <= tf - jl_eps(tc)) {                                   // timestepping.jl:104
         if (max_steps >= 0 && steps >= max_steps) { finished = false; break; }
         double dt_cfl;

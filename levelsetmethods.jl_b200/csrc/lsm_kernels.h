@@ -65,6 +65,25 @@ template <class T> cudaError_t launch_stage_pair3d(const StageParams<T>& P, cons
 // lsm_pair2d.cu (2-D WENO5 advection [+ constant-b curvature], x-pair threads marching along y)
 template <class T> cudaError_t launch_stage_pair2d(const StageParams<T>& P, const AuxList& A, cudaStream_t s, bool force, int sm_count);
 
+// lsm_resident2d.cu (small 2-D grids: the whole time loop of one stored-velocity WENO5 advection term in one cluster kernel)
+template <class T>
+struct ResidentArgs {
+    const T* phi;          // state, read once
+    T* out;                // state, written once (may alias phi)
+    const T* u[2];         // velocity components (same box as the state)
+    int n[2];
+    long s1;               // row stride (elements)
+    int bc[2][2];          // BC_* kinds (index maps only)
+    double h[2];
+    int nstages;           // 1 ForwardEuler, 2 RK2, 3 TVD-RK3
+    int nruns;             // run-length encoded step sizes: count[r] steps of dt[r]
+    double dt[4];
+    long count[4];
+    WenoK wk;
+};
+template <class T> bool resident2d_supported(int n0, int n1);
+template <class T> cudaError_t launch_resident2d(const ResidentArgs<T>& R, cudaStream_t s);
+
 // lsm_tiled.cu (performance kernels).  Returns cudaErrorNotSupported when the configuration is
 // not covered, in which case the caller uses the generic kernel.
 template <class T> cudaError_t launch_stage_tiled(int ndim, const StageParams<T>& P, int sm_count, cudaStream_t s, int pair_mode = 1, int* used_pair = nullptr);   // pair_mode: 0 never, 1 x-pair kernels (3-D: 20-bit eps max), 2 3-D x-pair kernel with the exact eps max, 3 x-pair kernels forced on small 2-D grids too

@@ -374,6 +374,68 @@ def test_pair2d_kernel_vs_tiled(m, n):
                 assert d <= (1e-13 if dtype == np.float64 else 1e-6), (n, bc, np.dtype(dtype).name, curv, integ.__name__, d)
 
 
+@pytest.mark.parametrize("n", [(128, 128), (40, 48), (130, 49), (33, 70), (170, 170), (8, 300)], ids=["128x128", "40x48", "130x49", "33x70", "170x170", "8x300"])
+def test_resident_kernel_bitwise_vs_tiled(m, n):
+    """Small 2-D grids run the WHOLE time loop in one cluster kernel (csrc/lsm_resident2d.cu: state, stage buffers and velocity in
+    the distributed shared memory of 16 CTAs, every result pushed into the ghost columns / the neighbouring CTAs' halo rows that
+    mirror it, the dt sequence replayed on the host).  Same arithmetic as the tiled 2-D kernel (LSM_OPT_KERNEL = 3), so time,
+    step count and state must be BIT-IDENTICAL: every index-map BC, FE / RK2 / RK3, both dtypes, strips of exactly 3 rows
+    (40x48), uneven strips (130x49: 4 rows and 3 rows), 2 and 4 nodes per thread, a final step shorter than the others (two
+    dt runs), sign changes of the velocity."""
+    ctx = m.default_context()
+    lc, hc = (-1.0, -1.0), (1.0, 1.0)
+    x, y = H.coords(lc, hc, n)
+    phi = np.hypot(x - 0.1, y + 0.05) - 0.45 + 0.03 * np.sin(9 * x) * np.cos(7 * y)
+    u = np.stack([H.bcast(-y + 0.2 * np.sin(5 * x), n), H.bcast(x + 0.1 * np.cos(4 * y), n)], axis=0)
+    bcs = [("periodic",), ("neumann",), ("symmetry",), ((("neumann",), ("symmetry",)), ("periodic",)),
+           (("periodic",), (("symmetry",), ("neumann",)))]
+    k = 0
+    for bc in bcs:
+        for dtype in (np.float64, np.float32):
+            k += 1
+            case = H.Case("R2", lc, hc, n, phi, [dict(kind="advection", field=u)], bc, dtype)
+            integ = (m.RK3, m.RK2, m.ForwardEuler)[k % 3]
+            outs = []
+            for kernel in (0, 3):                      # 0: automatic selection (resident kernel), 3: tiled per-stage kernels
+                ctx.set_option(OPT_KERNEL, kernel)
+                ctx.reset_counters()
+                f = case.engine_field(m)
+                eq = m.LevelSetEquation(terms=case.engine_terms(m, f), ic=f, integrator=integ())
+                dt = 0.5 * m.compute_cfl(eq.terms, eq.state, 0.0)
+                m.integrate(eq, 6.4 * dt)
+                n1 = eq.steps_taken
+                m.integrate(eq, 9.0 * dt)                # a second call starts from the state the first one left on the device
+                c = ctx.counters()
+                outs.append((eq.t, (n1, eq.steps_taken), eq.state.peek().copy(), c["resident_steps"], c["stage_launches"]))
+            ctx.set_option(OPT_KERNEL, 0)
+            assert outs[0][3] == sum(outs[0][1]) >= 9 and outs[0][4] == 0 and outs[1][3] == 0, ("kernel selection", outs[0][3:], outs[1][3:])
+            assert outs[0][:2] == outs[1][:2], (outs[0][:2], outs[1][:2])
+            assert np.array_equal(outs[0][2], outs[1][2]), (n, bc, np.dtype(dtype).name, integ.__name__,
+                                                            np.abs(outs[0][2].astype(np.float64) - outs[1][2].astype(np.float64)).max())
+
+
+def test_resident_kernel_c1_long_run(m):
+    """BASELINE configs[0] (128^2 circle rotation, periodic, Float64 RK3) for 300 steps through the resident cluster kernel against
+    the per-stage tiled kernels (bit-identical) — and the options that must switch it off do."""
+    ctx = m.default_context()
+    case = H.c1_circle_rotation(128)
+    outs = []
+    for kernel, resident in ((0, 1), (3, 1), (0, 0)):
+        ctx.set_option(OPT_KERNEL, kernel)
+        ctx.set_option(m._lib.OPT_RESIDENT, resident)
+        ctx.reset_counters()
+        f = case.engine_field(m)
+        eq = m.LevelSetEquation(terms=case.engine_terms(m, f), ic=f, integrator=m.RK3())
+        dt = 0.5 * m.compute_cfl(eq.terms, eq.state, 0.0)
+        m.integrate(eq, 300 * dt * (1 - 1e-12))
+        outs.append((eq.t, eq.steps_taken, eq.state.peek().copy(), ctx.counters()["resident_steps"]))
+    ctx.set_option(OPT_KERNEL, 0)
+    ctx.set_option(m._lib.OPT_RESIDENT, 1)
+    assert outs[0][3] == 300 and outs[1][3] == 0 and outs[2][3] == 0
+    for o in outs[1:]:
+        assert o[:2] == outs[0][:2] and np.array_equal(o[2], outs[0][2])
+
+
 @pytest.mark.parametrize("n", [(128, 64, 40), (72, 52, 37), (64, 8, 8)], ids=["128x64x40", "72x52x37", "64x8x8"])
 def test_pair_kernel_eikonal_bitwise_vs_tiled(m, n):
     """BASELINE config 4's term (EikonalReinitializationTerm with a frozen stored S0) through the x-pair kernel: the same
@@ -855,27 +917,32 @@ def test_graph_replay_is_invisible(m, O):
     final shorter step (different dt -> direct launches) and a second integrate! call on the same equation."""
     ctx = m.default_context()
     OPT_GRAPH = m._lib.OPT_GRAPH
-    for mk, integ in ((lambda: H.c1_circle_rotation(64), m.RK3), (lambda: H.c2_zalesak_curvature(96), m.RK2),
-                      (lambda: H.c5_normal_advection(24), m.RK3)):
-        res = []
-        for on in (1, 0):
-            ctx.set_option(OPT_GRAPH, on)
-            case = mk()
-            phi = case.engine_field(m)
-            eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=integ())
-            dt0 = 0.5 * m.compute_cfl(eq.terms, eq.state, 0.0)
-            ctx.reset_counters()
-            m.integrate(eq, dt0 * 17.3)               # 17 full steps + one shorter
-            n1 = eq.steps_taken
-            m.integrate(eq, dt0 * 25.0)
-            c = ctx.counters()
-            res.append((eq.state.peek().copy(), eq.t, n1, eq.steps_taken, c["kernel_launches"], c["stage_launches"]))
+    ctx.set_option(m._lib.OPT_RESIDENT, 0)            # the resident cluster kernel would take the first case whole
+    try:
+        for mk, integ in ((lambda: H.c1_circle_rotation(64), m.RK3), (lambda: H.c2_zalesak_curvature(96), m.RK2),
+                          (lambda: H.c5_normal_advection(24), m.RK3)):
+            res = []
+            for on in (1, 0):
+                ctx.set_option(OPT_GRAPH, on)
+                case = mk()
+                phi = case.engine_field(m)
+                eq = m.LevelSetEquation(terms=case.engine_terms(m, phi), ic=phi, integrator=integ())
+                dt0 = 0.5 * m.compute_cfl(eq.terms, eq.state, 0.0)
+                ctx.reset_counters()
+                m.integrate(eq, dt0 * 17.3)               # 17 full steps + one shorter
+                n1 = eq.steps_taken
+                m.integrate(eq, dt0 * 25.0)
+                c = ctx.counters()
+                res.append((eq.state.peek().copy(), eq.t, n1, eq.steps_taken, c["kernel_launches"], c["stage_launches"]))
+            ctx.set_option(OPT_GRAPH, 1)
+            assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:], res[0][1:]
+            fo = mk().oracle_field()
+            O.integrate(fo, {m.RK3: O.RK3, m.RK2: O.RK2}[integ], mk().oracle_terms(), res[0][1])
+            # two integrate calls vs one oracle call to the same final time: the step sequences differ, so compare loosely
+            assert np.abs(res[0][0] - fo.vals).max() < 1e-3
+    finally:
         ctx.set_option(OPT_GRAPH, 1)
-        assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:], res[0][1:]
-        fo = mk().oracle_field()
-        O.integrate(fo, {m.RK3: O.RK3, m.RK2: O.RK2}[integ], mk().oracle_terms(), res[0][1])
-        # two integrate calls vs one oracle call to the same final time: the step sequences differ, so compare loosely
-        assert np.abs(res[0][0] - fo.vals).max() < 1e-3
+        ctx.set_option(m._lib.OPT_RESIDENT, 1)
 
 
 @pytest.mark.parametrize("integ", ["RK3", "RK2", "FE"])

@@ -73,7 +73,8 @@ def run(name, case, integ, balg, steps, warmup=3, reps=5):
     out = {"config": name, "grid": list(case.n), "dtype": np.dtype(case.dtype).name, "integrator": type(integ).__name__,
            "steps": steps, "reps": len(runs), "ms_per_step_min_max": [runs[0][0] / steps, runs[-1][0] / steps], "ms_per_step": ms / steps, "cell_updates_per_s": ups, "avg_stage_launch_ms": stage_ms,
            "algorithmic_bytes_per_update": balg, "achieved_gbs": ach, "peak_gbs": peak(), "frac": ach / peak(),
-           "step_frac_of_roofline": ups * balg / 1e9 / peak(), "kernel_launches": cnt["kernel_launches"], "cfl_passes": cnt["cfl_passes"]}
+           "step_frac_of_roofline": ups * balg / 1e9 / peak(), "kernel_launches": cnt["kernel_launches"], "cfl_passes": cnt["cfl_passes"],
+           "resident_steps": cnt0.get("resident_steps", 0)}
     print(json.dumps(out), flush=True)
     del eq, phi, terms, low
 
