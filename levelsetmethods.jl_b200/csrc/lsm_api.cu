@@ -515,6 +515,8 @@ int32_t run_resident(lsm_ctx* ctx, int integ, lsm_field* phi, const lsm_term& te
     R.s1 = phi->n[0];
     R.nstages = nstages(integ);
     R.wk = weno_constants();
+    R.status = ctx->d_scalar + 2;
+    CU(cudaMemsetAsync(R.status, 0, 8, ctx->stream));
     int64_t done = 0;
     for (size_t i = 0; i < runs.size(); i += 4) {
         R.nruns = (int)std::min<size_t>(4, runs.size() - i);
@@ -527,6 +529,10 @@ int32_t run_resident(lsm_ctx* ctx, int integ, lsm_field* phi, const lsm_term& te
         ctx->cnt.kernel_launches += 1; ctx->cnt.resident_steps += here;
     }
     phi->version++; phi->halo_valid = true;
+    CU(cudaMemcpyAsync(ctx->h_scalar + 2, R.status, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));                    // lsm_integrate returns synchronised anyway
+    ctx->cnt.d2h_bytes += 8;
+    if (ctx->h_scalar[2] != 0ULL) return fail(LSM_ERR_CUDA, "resident kernel: halo protocol failure (status %llu); the state is not valid", ctx->h_scalar[2]);
     return LSM_OK;
 }
 

@@ -80,6 +80,7 @@ struct ResidentArgs {
     double dt[4];
     long count[4];
     WenoK wk;
+    unsigned long long* status;   // device word, zeroed by the caller: != 0 after the run = internal protocol failure (never expected)
 };
 template <class T> bool resident2d_supported(int n0, int n1);
 template <class T> cudaError_t launch_resident2d(const ResidentArgs<T>& R, cudaStream_t s);

@@ -11,8 +11,10 @@
 //     node under the boundary conditions' index maps — is worked out once;
 //   * a stage = evaluate the owned nodes with the arithmetic of the tiled 2-D kernel (lsm_tiled.cu: promoted Float64 WENO5, same
 //     operation order -> bit-identical results), store the result into the own buffer AND PUSH it into the ghost columns / the
-//     neighbouring CTAs' halo rows that mirror it (DSMEM stores through cluster.map_shared_rank), then ONE cluster barrier
-//     (release / acquire): no fetch phase, no other synchronisation;
+//     neighbouring CTAs' halo rows that mirror it with st.async (a DSMEM store that counts its bytes on the destination CTA's
+//     mbarrier): a stage ends with __syncthreads + a wait for the 6 * n0 halo values of the own strip — point-to-point, no
+//     cluster-wide barrier and no memory fence (a cluster barrier with release semantics costs MEMBAR.ALL.GPU + ~500 cycles:
+//     20 % of the first version's time);
 //   * the host knows every dt in advance (static velocity: dt = min(dt_max, cfl * dt_cfl, tf - tc), timestepping.jl:104-118), so
 //     the kernel receives the run-length encoded dt sequence and touches global memory twice: at the start and at the end.
 //
@@ -41,6 +43,51 @@ __device__ inline int strip_owner(int row, int n1) {
     return row < r * (b + 1) ? row / (b + 1) : r + (row - r * (b + 1)) / b;
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, int rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// remote store that signals the destination CTA's mbarrier (complete_tx) when the datum has landed
+__device__ __forceinline__ void st_async(unsigned raddr, double v, unsigned rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(raddr), "l"(__double_as_longlong(v)), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void st_async(unsigned raddr, float v, unsigned rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(raddr), "r"(__float_as_uint(v)), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Wait for a phase of the CTA's halo mbarrier.  The protocol cannot dead-lock (see the kernel), but a resident kernel that spins
+// for ever would take the whole device with it, so the wait is bounded: after ~2 s (or as soon as another thread has given up)
+// the status word is set, every later wait returns at once and the host reports the failure.
+__device__ __noinline__ void mbar_wait_slow(unsigned bar, unsigned parity, unsigned long long* status, bool& dead) {
+    const long long t0 = clock64();
+    long long next = 1LL << 20;
+    for (;;) {
+        if (mbar_try_wait(bar, parity)) return;
+        const long long el = clock64() - t0;
+        if (el > next) {
+            next = el + (1LL << 20);
+            if (*reinterpret_cast<volatile unsigned long long*>(status) != 0ULL) { dead = true; return; }
+            if (el > (1LL << 32)) { atomicMax(status, 2ULL); dead = true; return; }
+        }
+    }
+}
+__device__ __forceinline__ void mbar_wait_guarded(unsigned bar, unsigned parity, unsigned long long* status, bool& dead) {
+    if (dead) return;
+#pragma unroll 1
+    for (int i = 0; i < 16; ++i) if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(bar, parity, status, dead);
+}
+
 template <class T, int NPT>
 __global__ void __launch_bounds__(RES_NT, 1) resident2d_kernel(const __grid_constant__ ResidentArgs<T> R) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -52,7 +99,8 @@ __global__ void __launch_bounds__(RES_NT, 1) resident2d_kernel(const __grid_cons
     const int r_beg = strip_begin(rank, n1), rows = strip_rows(rank, n1), nodes = rows * n0;
     const int BUF = (RMAX + 2 * HAL) * W;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* const A0 = reinterpret_cast<double*>(smem_raw);  // |u_x| / h_x of the owned nodes, [RMAX * n0]
+    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(smem_raw);      // [2] halo mbarriers (even / odd stages)
+    double* const A0 = reinterpret_cast<double*>(smem_raw + 16);   // |u_x| / h_x of the owned nodes, [RMAX * n0]
     double* const A1 = A0 + RMAX * n0;                       // |u_y| / h_y
     T* const U = reinterpret_cast<T*>(A1 + RMAX * n0);       // [3][RMAX + 6][W]
     int* const hcnt = reinterpret_cast<int*>(U + 3 * BUF);   // [RMAX] halo-row destinations of each owned row
@@ -61,6 +109,7 @@ __global__ void __launch_bounds__(RES_NT, 1) resident2d_kernel(const __grid_cons
 
     // ---- which halo rows of the cluster mirror my rows (boundaryconditions.jl:107-153 as index maps, meshfield.jl:248-260)
     for (int r = tid; r < RMAX; r += RES_NT) hcnt[r] = 0;
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
     __syncthreads();
     if (tid < RES_CS * 2 * HAL) {
         const int q = tid / (2 * HAL), j = tid - q * (2 * HAL);
@@ -72,6 +121,7 @@ __global__ void __launch_bounds__(RES_NT, 1) resident2d_kernel(const __grid_cons
             const int lr = gr - r_beg;
             const int slot = atomicAdd(&hcnt[lr], 1);
             if (slot < RES_MAXD) hdst[lr * RES_MAXD + slot] = (q << 16) | (rel + HAL);
+            else atomicMax(R.status, 1ULL);                  // cannot happen when every strip has >= 3 rows
         }
     }
     __syncthreads();
@@ -103,8 +153,10 @@ __global__ void __launch_bounds__(RES_NT, 1) resident2d_kernel(const __grid_cons
         }
     }
 
-    // store a node value: own buffer, the ghost columns and the halo rows (of any CTA) that mirror it
-    auto put = [&](T* buf, const int sc, const unsigned inf, const int xr, const T val) {
+    // store a node value: own buffer, the ghost columns, and the halo rows (of any CTA) that mirror it — those with st.async,
+    // which counts the bytes on the destination CTA's mbarrier `rb`
+    const unsigned bar_u32 = smem_u32(bar);
+    auto put = [&](T* buf, const int sc, const unsigned inf, const int xr, const T val, const unsigned rb) {
         buf[sc] = val;
         if (inf & 0x7FCu) {
             const int x = xr & 0xFFFF, row = xr >> 16;
@@ -117,20 +169,35 @@ __global__ void __launch_bounds__(RES_NT, 1) resident2d_kernel(const __grid_cons
             const int nd = (inf >> 8) & 7;
             for (int j = 0; j < nd; ++j) {
                 const int d = hdst[row * RES_MAXD + j];
-                T* const rp = cluster.map_shared_rank(buf, d >> 16) + (d & 0xFFFF) * W + 4 + x;
-                *rp = val;
+                const unsigned la = smem_u32(buf) + (unsigned)(((d & 0xFFFF) * W + 4 + x) * (int)sizeof(T));
+                st_async(mapa_u32(la, d >> 16), val, mapa_u32(rb, d >> 16));
             }
         }
     };
+    // End of a stage: own stores visible to the CTA (__syncthreads), all 6 * n0 halo values of the buffer just written have
+    // arrived from their owners (mbarrier of the stage's parity).  No cluster-wide barrier: a CTA can be at most one stage ahead
+    // of the CTAs it exchanges rows with (it needs their rows of the previous stage), it pushes into a buffer they read two
+    // stages ago at the latest — or, for RK2's corrector, into halo rows whose readers are exactly the threads whose pushes it
+    // has waited for — and the even / odd mbarriers keep the byte counts of consecutive stages apart.
+    const unsigned halo_bytes = (unsigned)(2 * HAL * n0 * (int)sizeof(T));
+    unsigned gstage = 0;
+    bool dead = false;
+    auto stage_end = [&]() {
+        const unsigned b = bar_u32 + 8u * (gstage & 1u);
+        __syncthreads();
+        if (tid == 0) mbar_expect_tx(bar + (gstage & 1u), halo_bytes);
+        mbar_wait_guarded(b, (gstage >> 1) & 1u, R.status, dead);
+        ++gstage;
+    };
 
-    cluster.sync();                                          // every CTA of the cluster is running: its shared memory may be written
+    cluster.sync();                                          // every CTA of the cluster is running and has initialised its mbarriers
 #pragma unroll
     for (int k = 0; k < NPT; ++k)
         if (tid + k * RES_NT < nodes) {
             const int x = nxr[k] & 0xFFFF, row = nxr[k] >> 16;
-            put(U, nsc[k], ninf[k], nxr[k], R.phi[(long)(r_beg + row) * R.s1 + x]);
+            put(U, nsc[k], ninf[k], nxr[k], R.phi[(long)(r_beg + row) * R.s1 + x], bar_u32);
         }
-    cluster.sync();
+    stage_end();
 
     const WenoK& K = R.wk;
     const int nst = R.nstages;
@@ -155,6 +222,7 @@ __global__ void __launch_bounds__(RES_NT, 1) resident2d_kernel(const __grid_cons
                     if (s == 0) { in = a; out = b; out2 = c; c2 = 0.5 * dt; }
                     else { in = b; out = a; p0 = c; base = BASE_P0; cc = 0.5 * dt; }
                 } else { in = a; out = b; }
+                const unsigned rbar = bar_u32 + 8u * (gstage & 1u);
 #pragma unroll
                 for (int k = 0; k < NPT; ++k) {
                     if (tid + k * RES_NT < nodes) {
@@ -172,16 +240,17 @@ __global__ void __launch_bounds__(RES_NT, 1) resident2d_kernel(const __grid_cons
                         if (base == BASE_RK3_S2) xb = T(fma(0.75, double(p0[sc]), 0.25 * double(qc)));     // timestepping.jl:183
                         else if (base == BASE_RK3_S3) xb = div3(T(p0[sc] + T(2) * qc));                      // timestepping.jl:194
                         else if (base == BASE_P0) xb = p0[sc];                                               // RK2 corrector
-                        put(out, sc, inf, nxr[k], T(fma(-cc, H, double(xb))));
+                        put(out, sc, inf, nxr[k], T(fma(-cc, H, double(xb))), rbar);
                         if (out2) out2[sc] = T(fma(-c2, H, double(qc)));
                     }
                 }
-                cluster.sync();
+                stage_end();
             }
             if (nst == 1) cur = cur == 2 ? 0 : cur + 1;      // ForwardEuler: the output buffer becomes the state
         }
     }
 
+    cluster.sync();                                          // nobody exits while a neighbour may still address its shared memory
     const T* const fin = U + cur * BUF;
 #pragma unroll
     for (int k = 0; k < NPT; ++k)
@@ -194,7 +263,7 @@ __global__ void __launch_bounds__(RES_NT, 1) resident2d_kernel(const __grid_cons
 template <class T>
 size_t resident_smem(int n0, int n1) {
     const size_t rmax = (size_t)(n1 + RES_CS - 1) / RES_CS;
-    return 2 * rmax * n0 * sizeof(double) + 3 * (rmax + 2 * HAL) * (n0 + 8) * sizeof(T) + rmax * (1 + RES_MAXD) * sizeof(int);
+    return 2 * rmax * n0 * sizeof(double) + 3 * (rmax + 2 * HAL) * (n0 + 8) * sizeof(T) + 16 + rmax * (1 + RES_MAXD) * sizeof(int);
 }
 
 }  // namespace
