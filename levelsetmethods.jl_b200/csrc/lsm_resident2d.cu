@@ -88,7 +88,7 @@ __device__ __forceinline__ void mbar_wait_guarded(unsigned bar, unsigned parity,
     mbar_wait_slow(bar, parity, status, dead);
 }
 
-template <class T, int NPT>
+template <class T, int NPT, int NST>
 __global__ void __launch_bounds__(RES_NT, 1) resident2d_kernel(const __grid_constant__ ResidentArgs<T> R) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -200,7 +200,9 @@ __global__ void __launch_bounds__(RES_NT, 1) resident2d_kernel(const __grid_cons
     stage_end();
 
     const WenoK& K = R.wk;
-    const int nst = R.nstages;
+    // stages per step: compile-time in the 2-nodes-per-thread kernels, so the buffer roles of a stage are too (NST = 0: runtime —
+    // with 4 nodes per thread the unrolled stages would spill)
+    const int nst = NST > 0 ? NST : R.nstages;
     int cur = 0;                                             // buffer holding the state
     for (int r = 0; r < R.nruns; ++r) {
         const double dt = R.dt[r];
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(RES_NT, 1) resident2d_kernel(const __grid_cons
             T* const a = U + cur * BUF;
             T* const b = U + (cur == 2 ? 0 : cur + 1) * BUF;
             T* const c = U + (cur == 0 ? 2 : cur - 1) * BUF;
+#pragma unroll(NST > 0 ? NST : 1)
             for (int s = 0; s < nst; ++s) {
                 // one RK stage: out = base(in, p0) - cc * H(in)   [out2 = in - c2 * H(in)]     (timestepping.jl:128-202)
                 T *in, *out, *out2 = nullptr;
@@ -279,7 +282,7 @@ bool resident2d_supported(int n0, int n1) {
 }
 
 namespace {
-template <class T, int NPT>
+template <class T, int NPT, int NST>
 cudaError_t launch_npt(const ResidentArgs<T>& R, cudaStream_t s) {
     const size_t smem = resident_smem<T>(R.n[0], R.n[1]);
     int dev = 0;
@@ -289,8 +292,8 @@ cudaError_t launch_npt(const ResidentArgs<T>& R, cudaStream_t s) {
     static bool ready[64] = {};
     if (dev < 0 || dev >= 64) return cudaErrorNotSupported;
     if (!ready[dev]) {
-        e = cudaFuncSetAttribute(resident2d_kernel<T, NPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(resident2d_kernel<T, NPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_MAX_SMEM);
+        e = cudaFuncSetAttribute(resident2d_kernel<T, NPT, NST>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(resident2d_kernel<T, NPT, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_MAX_SMEM);
         if (e != cudaSuccess) { cudaGetLastError(); return cudaErrorNotSupported; }
         ready[dev] = true;
     }
@@ -304,9 +307,9 @@ cudaError_t launch_npt(const ResidentArgs<T>& R, cudaStream_t s) {
     at[0].val.clusterDim.x = RES_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int ncl = 0;
-    e = cudaOccupancyMaxActiveClusters(&ncl, resident2d_kernel<T, NPT>, &cfg);          // a 16-CTA cluster needs one GPC with 16 free SMs
+    e = cudaOccupancyMaxActiveClusters(&ncl, resident2d_kernel<T, NPT, NST>, &cfg);          // a 16-CTA cluster needs one GPC with 16 free SMs
     if (e != cudaSuccess || ncl < 1) { cudaGetLastError(); return cudaErrorNotSupported; }
-    return cudaLaunchKernelEx(&cfg, resident2d_kernel<T, NPT>, R);
+    return cudaLaunchKernelEx(&cfg, resident2d_kernel<T, NPT, NST>, R);
 }
 }  // namespace
 
@@ -314,7 +317,13 @@ template <class T>
 cudaError_t launch_resident2d(const ResidentArgs<T>& R, cudaStream_t s) {
     if (!resident2d_supported<T>(R.n[0], R.n[1])) return cudaErrorNotSupported;
     const long per_cta = (long)((R.n[1] + RES_CS - 1) / RES_CS) * R.n[0];
-    return per_cta <= 2L * RES_NT ? launch_npt<T, 2>(R, s) : launch_npt<T, 4>(R, s);
+    const bool two = per_cta <= 2L * RES_NT;
+    switch (R.nstages) {
+        case 1: return two ? launch_npt<T, 2, 1>(R, s) : launch_npt<T, 4, 0>(R, s);
+        case 2: return two ? launch_npt<T, 2, 2>(R, s) : launch_npt<T, 4, 0>(R, s);
+        case 3: return two ? launch_npt<T, 2, 3>(R, s) : launch_npt<T, 4, 0>(R, s);
+        default: return cudaErrorNotSupported;
+    }
 }
 
 template bool resident2d_supported<double>(int, int);
