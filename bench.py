@@ -71,14 +71,17 @@ def build_c3(m, ctx, n, G):
     return grid, phi, vel, terms
 
 
-def build_c5(m, ctx, n):
+def build_c5(m, ctx, n, nz=None):
     """BASELINE.json configs[4] "C5" on the n^3 grid on (-1,-1,-1)..(1,1,1): phi0 = |x - (0.3,0,0)| - 0.4, NormalMotionTerm(v = 0.2
-    stored scalar field) + AdvectionTerm(u = (-y, x, 0) stored field), all generated on the device."""
-    grid = m.CartesianGrid((-1, -1, -1), (1, 1, 1), (n, n, n))
-    phi = m.MeshField.from_shape(grid, "sphere", (0.3, 0.0, 0.0, 0.4), bc=m.NeumannBC(), ctx=ctx)
+    stored scalar field) + AdvectionTerm(u = (-y, x, 0) stored field), all generated on the device.  nz != n (experiments: the slab
+    shape of an 8-GPU run on fewer GPUs) keeps the cells cubic by shortening the domain along z."""
+    nz = nz or n
+    h = 2.0 / (n - 1)
+    grid = m.CartesianGrid((-1, -1, -1), (1, 1, 1 if nz == n else -1 + (nz - 1) * h), (n, n, nz))
+    phi = m.MeshField.from_shape(grid, "sphere", (0.3, 0.0, 0.0 if nz == n else -1 + 0.5 * (nz - 1) * h, 0.4), bc=m.NeumannBC(), ctx=ctx)
     x = -1.0 + np.arange(n) * (2.0 / (n - 1))
-    one = np.ones(n)
-    rot = m.SeparableVelocity(grid, (-1.0, 1.0, 0.0), [[one, x, one], [x, one, one], [one, one, one]], ctx=ctx)
+    one, onez = np.ones(n), np.ones(nz)
+    rot = m.SeparableVelocity(grid, (-1.0, 1.0, 0.0), [[one, x, onez], [x, one, onez], [one, one, onez]], ctx=ctx)
     vel = m.MeshField.from_separable(rot, ctx=ctx)
     spd = m.MeshField.from_shape(grid, "const", (0.2,), ctx=ctx)
     return grid, phi, (m.NormalMotionTerm(spd), m.AdvectionTerm(vel, m.WENO5()))
@@ -268,6 +271,7 @@ def main():
     ap.add_argument("--n", "--size", dest="n", type=int, default=0,
                     help="nodes per axis (c3: per GPU, default 512; c5: global, default 1024); use --size under torchrun, whose own parser\n"
                          "rejects --n as an ambiguous abbreviation of --nnodes / --nproc-per-node")
+    ap.add_argument("--nz", type=int, default=0, help="c5 only (experiments): global node count along the decomposed axis, default = size")
     ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
                     help="c3 = headline (weak-scaled Enright advection); c5 = BASELINE configs[4], strong-scaled 1024^3 normal motion + advection")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -316,8 +320,8 @@ def main():
     if G > 1 and not args.no_extras:
         invariance = invariance_check(m, ctx, dist, rank, world, local)
     if c5:
-        grid, phi, terms = build_c5(m, ctx, n)
-        nz = n
+        grid, phi, terms = build_c5(m, ctx, n, args.nz or None)
+        nz = args.nz or n
         args.no_e2e = True
         args.no_cpu = True
     else:

@@ -87,6 +87,7 @@ struct lsm_ctx {
     unsigned long long* h_scalar = nullptr;     // pinned
     lsm_counters cnt{};
     int opt_kernel = 0, opt_time = 0, opt_cfl_cache = 1, opt_overlap = 1;
+    int interior_first = 0;     // LSM_B200_INTERIOR_FIRST (experiments): round-2's original launch order of the overlapped stage
     std::vector<CflCacheEntry> cfl_cache;
     std::vector<CflCand> cfl_cand;
     int opt_cand = 1;           // LSM_OPT_CFL_CANDIDATES
@@ -142,8 +143,12 @@ int32_t ctx_common_init(lsm_ctx* c) {
     if (prop.major < 10) return fail(LSM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", c->device, prop.major, prop.minor);
     c->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->comm, cudaStreamNonBlocking));
-    { int lo = 0, hi = 0; CU(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CU(cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, hi)); }
+    {   // the boundary-slab stream and the halo-exchange stream outrank the compute stream: their (small) grids are placed first
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->comm, cudaStreamNonBlocking, getenv("LSM_B200_INTERIOR_FIRST") ? lo : hi));
+        CU(cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, hi));
+    }
     CU(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_boundary, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
@@ -151,6 +156,7 @@ int32_t ctx_common_init(lsm_ctx* c) {
     CU(cudaMallocHost(&c->h_scalar, 64));
     if (getenv("LSM_B200_NO_FUSE_CFL")) c->opt_fuse_cfl = 0;
     if (getenv("LSM_B200_NO_OVERLAP")) c->opt_overlap = 0;
+    if (getenv("LSM_B200_INTERIOR_FIRST")) c->interior_first = 1;
     if (getenv("LSM_B200_NO_GRAPH")) c->opt_graph = 0;
     return LSM_OK;
 }
@@ -422,6 +428,11 @@ int32_t run_stage_t(lsm_ctx* c, lsm_field* in, lsm_field* p0, lsm_field* out, ls
         CU(cudaStreamWaitEvent(c->comm, c->ev_boundary, 0));
         TRY(exchange_halo(out, c->comm));
         CU(cudaEventRecord(c->ev_halo, c->comm));
+        // The interior launch waits for the slabs too: they fill the GPU anyway (thousands of blocks), and the exchange kernel
+        // (a few blocks of NCCL's, more registers per block than an SM has left beside a resident interior block) then becomes
+        // runnable TOGETHER with the interior grid and — on a higher-priority stream — is placed first; launched behind an
+        // interior grid that already occupies every SM it would only run in that grid's tail, i.e. not overlapped at all.
+        if (!c->interior_first) CU(cudaStreamWaitEvent(c->stream, c->ev_boundary, 0));
         TRY(launch_stage_range<T>(c, in->ndim, P, sl, nl - sl));
         CU(cudaStreamWaitEvent(c->stream, c->ev_boundary, 0));
         CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
