@@ -155,6 +155,14 @@ int32_t lsm_host_unregister(void* ptr);
  * first_out is 0-based. */
 int32_t lsm_slab_plan(int32_t n_last, int32_t nranks, int32_t rank, int32_t* first_out, int32_t* count_out);
 
+/* Pure host function (no GPU needed): the step sizes the time loop takes when the CFL step dt_cfl is CONSTANT (static coefficients), i.e.
+ * the loop of _integrate! (timestepping.jl:104-118) replayed with its own arithmetic: while t <= tf - eps(t): dt = min(dt_max, cfl * dt_cfl,
+ * tf - t); t += dt — at most max_steps steps (< 0: no limit).  The sequence is run-length encoded into dt_out / count_out (capacity cap;
+ * cap = 0 only counts): normally two runs, n full steps and one shorter final step.  This is what lsm_integrate hands to the resident
+ * cluster kernel of small 2-D grids (LSM_OPT_RESIDENT); t_out / steps_out are the time and step count that loop reaches. */
+int32_t lsm_step_plan(double t0, double tf, double dt_max, double cfl, double dt_cfl, int64_t max_steps, int32_t cap,
+                      double* dt_out, int64_t* count_out, int32_t* nruns_out, int64_t* steps_out, double* t_out);
+
 /* ---- grid + field : CartesianGrid (meshes.jl:1-5,34-42) + MeshField (meshfield.jl:51-55) ------ */
 /* n = GLOBAL node counts.  ncomp = 1 (scalar) or ndim (velocity).  The field owns its device
  * memory (and, for a state field, the RK stage buffers of _alloc_buffers, timestepping.jl:126,141,168). */

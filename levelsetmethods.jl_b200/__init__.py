@@ -10,7 +10,7 @@ from ._lib import LSMError, CFLError, TimeError, BCError, build
 from .api import (Context, MultiContext, integrate_multi, compute_cfl_multi, default_context, set_default_context, CartesianGrid, BoundaryCondition, PeriodicBC,
                   ExtrapolationBC, NeumannBC, LinearExtrapolationBC, SymmetryBC, MeshField, Upwind, WENO5,
                   TimeScaled, SeparableVelocity, LevelSetTerm, AdvectionTerm, CurvatureTerm, NormalMotionTerm,
-                  EikonalReinitializationTerm, update_term, compute_cfl, TimeIntegrator, ForwardEuler, RK2, RK3,
+                  EikonalReinitializationTerm, update_term, compute_cfl, step_plan, TimeIntegrator, ForwardEuler, RK2, RK3,
                   LevelSetEquation, current_state, current_time, integrate, integrate_bang, volume, perimeter, eikonal_reinitialize, extend_along_normals,
     union, union_, intersect, intersect_, setdiff, setdiff_, complement, complement_,
                   _normalize_bc, _add_boundary_conditions)

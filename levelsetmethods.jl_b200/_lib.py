@@ -85,6 +85,7 @@ SYMBOLS = {
     "lsm_host_register": (_i32, [_vp, _i64]),
     "lsm_host_unregister": (_i32, [_vp]),
     "lsm_slab_plan": (_i32, [_i32, _i32, _i32, _pi32, _pi32]),
+    "lsm_step_plan": (_i32, [_dbl, _dbl, _dbl, _dbl, _dbl, _i64, _i32, _pdbl, C.POINTER(C.c_int64), _pi32, C.POINTER(C.c_int64), _pdbl]),
     "lsm_field_create": (_i32, [_vp, _i32, _pi32, _i32, _i32, _pdbl, _pdbl, C.POINTER(_vp)]),
     "lsm_field_create_separable": (_i32, [_vp, _i32, _pi32, _pdbl, _pdbl, _pdbl, _pdbl, C.POINTER(_vp)]),
     "lsm_field_destroy": (_i32, [_vp]),

@@ -750,6 +750,18 @@ class _Lowered:
                 d.cval[i] = float(c_)
 
 
+def step_plan(t0: float, tf: float, dt_max: float, cfl: float, dt_cfl: float, max_steps: int = -1):
+    """The step sizes ``_integrate!`` takes when the CFL step is constant (timestepping.jl:104-118), run-length encoded:
+    ``(runs, steps, t_reached)`` with ``runs = [(dt, count), ...]``.  Pure host function (``lsm_step_plan``); this is the sequence
+    ``lsm_integrate`` hands to the resident cluster kernel of small 2-D grids."""
+    lib = L.lib()
+    nr, st, tt = C.c_int32(), C.c_int64(), C.c_double()
+    L.check(lib.lsm_step_plan(t0, tf, dt_max, cfl, dt_cfl, max_steps, 0, None, None, C.byref(nr), C.byref(st), C.byref(tt)))
+    dts, cnt = (C.c_double * max(nr.value, 1))(), (C.c_int64 * max(nr.value, 1))()
+    L.check(lib.lsm_step_plan(t0, tf, dt_max, cfl, dt_cfl, max_steps, nr.value, dts, cnt, C.byref(nr), C.byref(st), C.byref(tt)))
+    return [(dts[i], cnt[i]) for i in range(nr.value)], st.value, tt.value
+
+
 def compute_cfl(terms, phi: MeshField, t: float) -> float:
     """``compute_cfl(terms, phi, t)`` (levelsetterms.jl:22-38); raises :class:`CFLError` unless ``dt > 0``."""
     low = _Lowered(terms, phi, t)

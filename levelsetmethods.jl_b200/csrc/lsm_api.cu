@@ -493,6 +493,21 @@ int32_t stage_impl(lsm_ctx* ctx, int integ, int stage, lsm_field* phi, const lsm
 
 int nstages(int integ) { return integ == LSM_FORWARD_EULER ? 1 : integ == LSM_RK2 ? 2 : 3; }
 
+// The step sizes of the time loop for a CONSTANT CFL step dt_cfl (static coefficients), replayed with the loop's own arithmetic
+// (timestepping.jl:104-118): while t <= tf - eps(t): dt = min(dt_max, cfl * dt_cfl, tf - t); t += dt.  Run-length encoded; stops
+// after `limit` steps (< 0: none).  Returns the time reached and the number of steps.
+void plan_steps(double t0, double tf, double dt_max, double cfl, double dt_cfl, int64_t limit,
+                std::vector<std::pair<double, long>>& runs, double* t_end, int64_t* nsteps) {
+    const double D = jl_min(dt_max, cfl * dt_cfl);
+    double t = t0; int64_t n = 0;
+    while (t <= tf - jl_eps(t) && (limit < 0 || n < limit)) {
+        const double dt = jl_min(D, tf - t);                       // timestepping.jl:111
+        if (!runs.empty() && runs.back().first == dt) runs.back().second++; else runs.emplace_back(dt, 1L);
+        t += dt; ++n;
+    }
+    *t_end = t; *nsteps = n;
+}
+
 // lsm_resident2d.cu covers: single rank, 2-D, ONE AdvectionTerm(stored velocity of the state's dtype, WENO5) without a time factor,
 // index-map boundary conditions (periodic / Neumann / symmetry), automatic kernel selection, no per-stage timing
 bool resident_eligible(const lsm_ctx* ctx, const lsm_field* phi, const lsm_term* terms, int nterms) {
@@ -1011,6 +1026,23 @@ int32_t lsm_slab_plan(int32_t n_last, int32_t nranks, int32_t rank, int32_t* fir
     return LSM_OK;
 }
 
+int32_t lsm_step_plan(double t0, double tf, double dt_max, double cfl, double dt_cfl, int64_t max_steps, int32_t cap,
+                      double* dt_out, int64_t* count_out, int32_t* nruns_out, int64_t* steps_out, double* t_out) {
+    if (!nruns_out || !steps_out || !t_out || cap < 0 || (cap > 0 && (!dt_out || !count_out))) return fail(LSM_ERR_ARG, "bad step plan arguments");
+    if (!(tf >= t0)) return fail(LSM_ERR_TIME, "final time %g must be >= initial time %g: the level-set equation cannot be solved back in time", tf, t0);
+    const double D = jl_min(dt_max, cfl * dt_cfl);
+    if (!(std::isfinite(D) && D > 0.0) && t0 <= tf - jl_eps(t0)) return fail(LSM_ERR_ARG, "step plan needs a finite positive step (got %g)", D);
+    std::vector<std::pair<double, long>> runs;
+    double t = t0; int64_t n = 0;
+    constexpr int64_t PLAN_CAP = 1LL << 26;                        // a step that does not advance t must not loop for ever
+    plan_steps(t0, tf, dt_max, cfl, dt_cfl, max_steps < 0 ? PLAN_CAP : max_steps, runs, &t, &n);
+    if (max_steps < 0 && n >= PLAN_CAP) return fail(LSM_ERR_ARG, "step plan exceeds %lld steps", (long long)PLAN_CAP);
+    *nruns_out = (int32_t)runs.size(); *steps_out = n; *t_out = t;
+    if ((int64_t)runs.size() > cap) return cap == 0 ? LSM_OK : fail(LSM_ERR_ARG, "step plan has %zu runs, capacity %d", runs.size(), cap);
+    for (size_t i = 0; i < runs.size(); ++i) { dt_out[i] = runs[i].first; count_out[i] = runs[i].second; }
+    return LSM_OK;
+}
+
 int32_t lsm_field_create(lsm_ctx* ctx, int32_t ndim, const int32_t* n, int32_t dtype, int32_t ncomp,
                          const double* lc, const double* hc, lsm_field** out) {
     if (!ctx) return fail(LSM_ERR_ARG, "null context");
@@ -1291,11 +1323,7 @@ int32_t lsm_integrate(lsm_ctx* ctx, int32_t integrator, double cfl, lsm_field* p
             constexpr int64_t RES_STEP_CAP = 1 << 22;
             std::vector<std::pair<double, long>> runs;
             double t = tc; int64_t n = 0;
-            while (t <= tf - jl_eps(t) && n < RES_STEP_CAP && (max_steps < 0 || n < max_steps)) {
-                const double dt = jl_min(D, tf - t);                       // timestepping.jl:111
-                if (!runs.empty() && runs.back().first == dt) runs.back().second++; else runs.emplace_back(dt, 1L);
-                t += dt; ++n;
-            }
+            plan_steps(tc, tf, dt_max, cfl, dt_cfl, max_steps < 0 ? RES_STEP_CAP : std::min<int64_t>(max_steps, RES_STEP_CAP), runs, &t, &n);
             int32_t rr = phi->dtype == LSM_F64 ? run_resident<double>(ctx, integrator, phi, terms[0], runs)
                                                : run_resident<float>(ctx, integrator, phi, terms[0], runs);
             if (rr == LSM_OK) { tc = t; steps = n; }

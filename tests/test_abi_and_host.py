@@ -1,5 +1,5 @@
 """CPU-only checks: the C-ABI library loads and exports every symbol include/lsm_b200.h declares,
-host-side logic (grid, BC normalisation, slab plan) and loud failure without a GPU."""
+host-side logic (grid, BC normalisation, slab plan, step plan) and loud failure without a GPU."""
 import ctypes as C
 import os
 import re
@@ -73,6 +73,45 @@ def test_slab_plan(m):
         assert covered == list(range(n))
     f, c = C.c_int32(), C.c_int32()
     assert lib.lsm_slab_plan(10, 2, 2, C.byref(f), C.byref(c)) == m._lib.ERR_ARG
+
+
+def test_step_plan_replays_the_reference_loop(m):
+    """lsm_step_plan (pure host; what lsm_integrate hands to the resident cluster kernel of small 2-D grids) against a literal
+    transcription of _integrate!'s loop (timestepping.jl:104-118): same step sizes bit for bit, same step count, same final t —
+    for final times that are / are not multiples of the step, dt_max below and above the CFL step, a start time != 0, step limits."""
+    import math
+    import random
+
+    def reference(t0, tf, dt_max, cfl, dt_cfl, max_steps):
+        t, dts = t0, []
+        while t <= tf - math.ulp(t):                       # Base.eps(t) == ulp(t), eps(0.0) == 5e-324
+            if 0 <= max_steps <= len(dts):
+                break
+            dt = min(dt_max, cfl * dt_cfl, tf - t)
+            dts.append(dt)
+            t += dt
+        return dts, t
+
+    rng = random.Random(7)
+    cases = [(0.0, 1.0, math.inf, 0.5, 0.015625, -1), (0.0, 1.0, math.inf, 0.5, 0.0123, -1), (0.25, 0.25, math.inf, 0.5, 0.01, -1),
+             (0.0, 0.3, 0.004, 0.5, 0.0123, -1), (1.7, 2.9, math.inf, 0.9, 0.0371, 10), (0.0, 1e-3, math.inf, 0.5, 1.0, -1),
+             (0.0, 1.0, math.inf, 0.5, 0.0123, 0)]
+    for _ in range(40):
+        t0 = rng.choice([0.0, rng.uniform(0, 3)])
+        cases.append((t0, t0 + rng.uniform(0, 2), rng.choice([math.inf, rng.uniform(1e-3, 1e-1)]), rng.choice([0.5, 0.9, 1.0]),
+                      rng.uniform(1e-3, 0.2), rng.choice([-1, -1, 5, 200])))
+    for t0, tf, dt_max, cfl, dt_cfl, ms in cases:
+        runs, steps, t_end = m.step_plan(t0, tf, dt_max, cfl, dt_cfl, ms)
+        dts, t_ref = reference(t0, tf, dt_max, cfl, dt_cfl, ms)
+        flat = [dt for dt, c in runs for _ in range(c)]
+        assert flat == dts and steps == len(dts) and t_end == t_ref, (t0, tf, dt_max, cfl, dt_cfl, ms)
+        assert all(runs[i][0] != runs[i + 1][0] for i in range(len(runs) - 1))          # maximal runs
+        if ms < 0 and dts:
+            assert len(runs) <= 3 and abs(t_end - tf) <= 4 * math.ulp(tf)
+    with pytest.raises(m.TimeError):
+        m.step_plan(1.0, 0.5, math.inf, 0.5, 0.01)
+    with pytest.raises(m.LSMError):
+        m.step_plan(0.0, 1.0, math.inf, 0.5, float("nan"))
 
 
 # ---- test/test-meshes.jl ----
