@@ -19,3 +19,11 @@ K="python tools/bench_configs.py --steps 1 --warmup 0 --reps 1 --skip C1"
 timeout 600 $K > $O/cfg1.log 2>&1 && timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section ComputeWorkloadAnalysis --section SchedulerStats \
     --section WarpStateStats --section LaunchStats --section Occupancy --clock-control none -k "regex:stage_tiled|pair3d" -c 30 --csv --page raw \
     --log-file $O/ncu_kernels_$R.csv $K > $O/ncu_kernels.log 2>&1
+# the resident cluster kernel of small 2-D grids (C1): timing, then one full capture of the 200-step launch
+timeout 120 python tools/bench_configs.py --only C1 --reps 5 > $O/c1_resident.jsonl 2>&1
+K1="python tools/bench_configs.py --only C1 --steps 20 --warmup 0 --reps 1"
+timeout 120 $K1 > $O/c1_plain.log 2>&1 && timeout 200 ncu --set full --clock-control none --import-source on -k regex:resident2d -c 1 -f \
+    -o $O/prof_resident_$R $K1 > $O/ncu_resident.log 2>&1
+# the register-only FP64 floor of the WENO5 stage (build: see the header of tools/weno_floor.cu)
+[ -x tools/weno_floor ] && timeout 60 tools/weno_floor > $O/weno_floor_$R.txt
+# read here:  ncu -i X.ncu-rep --page raw --csv ;  ncu -i X.ncu-rep --page source --csv --print-source sass | python tools/ncu_opmix.py - NODES
