@@ -26,4 +26,4 @@ timeout 120 $K1 > $O/c1_plain.log 2>&1 && timeout 200 ncu --set full --clock-con
     -o $O/prof_resident_$R $K1 > $O/ncu_resident.log 2>&1
 # the register-only FP64 floor of the WENO5 stage (build: see the header of tools/weno_floor.cu)
 [ -x tools/weno_floor ] && timeout 60 tools/weno_floor > $O/weno_floor_$R.txt
-# read here:  ncu -i X.ncu-rep --page raw --csv ;  ncu -i X.ncu-rep --page source --csv --print-source sass | python tools/ncu_opmix.py - NODES
+# read here:  ncu -i X.ncu-rep --page raw --csv ;  ncu -i X.ncu-rep --page source --csv --print-source sass > src.csv ; python tools/ncu_opmix.py src.csv NODE_STAGES
